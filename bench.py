@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""Benchmark of the DoubleTake hot path on B200: depth frames/s at 640x480 image x 64 planes x 7 source views
+(BASELINE.json metric; cfg 2 = configs[1]).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU arm: the oracle port of the reference on the host cores
+
+One "step" = one pass of the hot path (relative poses -> fused hint cost volume -> CVEncoder -> DepthDecoderPP -> exp)
+over one batch (B=1 frame per rank) of synthetic input.  `value` = frames/s with inputs resident in HBM, device-timed
+with CUDA events (one event pair per step, L2 flushed between steps outside the timed intervals), max over ranks.
+`e2e` = the same metric through the public API `DepthModelCVHint.forward` fed from pinned HOST buffers (H2D of the
+step's inputs and D2H of the depth map inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from doubletake_b200 import synthetic as syn  # noqa: E402
+
+METRIC = "depth frames/sec at 640x480x64planes x7views"
+UNIT = "frames/s"
+WORKLOAD = "cfg2"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def algorithmic_bytes_cost_volume(cfg, hint=True):
+    """4*[(K+1)*C*H*W + 3*H*W + D*H*W + H*W] + H*W per frame."""
+    H, W, K, C, D = cfg.match_h, cfg.match_w, cfg.num_src, cfg.feat_ch, cfg.planes
+    return cfg.batch * (4 * ((K + 1) * C * H * W + (3 * H * W if hint else 0) + D * H * W + H * W) + H * W)
+
+
+def mlp_flops(cfg):
+    """2*H*W*D*(F*128 + 128*128 + 128 + 36 + 144 + 12) per frame."""
+    H, W, D, F = cfg.match_h, cfg.match_w, cfg.planes, cfg.mlp_in
+    return cfg.batch * 2 * H * W * D * (F * 128 + 128 * 128 + 128 + 36 + 144 + 12)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------------------------
+def host_inputs(cfg, seed):
+    """(cur_data, src_data) on the HOST, as DepthModelCVHint.forward consumes them, with the upstream encoders'
+    outputs (matching features, 5 image-prior maps) supplied precomputed."""
+    inp = syn.cost_volume_inputs(cfg, seed=seed)
+    priors = syn.prior_features(cfg, syn._gen(seed + 7))
+    eye = torch.eye(4).expand(cfg.batch, 4, 4).contiguous()
+    cur = {"cam_T_world_b44": eye, "world_T_cam_b44": eye.clone(), "invK_s1_b44": inp["cur_invK"],
+           "matching_feats_bchw": inp["cur_feats"], "image_prior_feats": priors}
+    cur.update({k: v for k, v in inp["cv_depth_hint_dict"].items() if v.dtype != torch.bool})
+    src = {"cam_T_world_b44": inp["src_extrinsics"], "world_T_cam_b44": inp["src_poses"], "K_s1_b44": inp["src_Ks"],
+           "matching_feats_bkchw": inp["src_feats"]}
+    return cur, src
+
+
+def tree_map(fn, d):
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, (list, tuple)):
+            out[k] = [fn(x) for x in v]
+        else:
+            out[k] = fn(v)
+    return out
+
+
+def tree_bytes(d):
+    n = 0
+    for v in d.values():
+        for x in (v if isinstance(v, (list, tuple)) else [v]):
+            n += x.numel() * x.element_size()
+    return n
+
+
+def model_weights(model, seed=2024):
+    shapes = {k: tuple(v.shape) for k, v in model.named_parameters()}
+    return syn.seeded_state_dict(shapes, seed, 1.3)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+
+    import doubletake_b200 as dt
+    from doubletake_b200 import _lib as L
+    from doubletake_b200 import sharding
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: doubletake_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_grad_enabled(False)
+
+    cfg = syn.CONFIGS[WORKLOAD]
+    opts = dt.HotPathOptions(matching_num_depth_bins=cfg.planes, model_num_views=cfg.num_src + 1,
+                             image_height=cfg.image_h, image_width=cfg.image_w)
+    model = dt.DepthModelCVHint(opts, math=args.math)
+    model.load_state_dict(model_weights(model), strict=False)
+    model = model.to(dev)
+
+    # a ring of distinct input sets (different seeds per rank and slot), resident in HBM and mirrored in pinned host memory
+    n_sets = 4
+    host_sets, dev_sets = [], []
+    for s in range(n_sets):
+        cur, src = host_inputs(cfg, cfg.seed + 100 * rank + s)
+        cur, src = tree_map(lambda t: t.pin_memory(), cur), tree_map(lambda t: t.pin_memory(), src)
+        host_sets.append((cur, src))
+        dev_sets.append((tree_map(lambda t: t.to(dev), cur), tree_map(lambda t: t.to(dev), src)))
+    h2d_bytes = tree_bytes(host_sets[0][0]) + tree_bytes(host_sets[0][1])
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    frames_per_step = cfg.batch * world
+    depth_shape = (cfg.batch, 1, cfg.image_h // 2, cfg.image_w // 2)
+    host_out = torch.empty(depth_shape, dtype=torch.float32).pin_memory()
+
+    def step_resident(i):
+        cur, src = dev_sets[i % n_sets]
+        out = model("test", cur, src, return_mask=True)
+        depth = out["depth_pred_s0_b1hw"]
+        if world > 1:
+            depth = sharding.gather_depth_maps(depth, frames_per_step)
+        return depth
+
+    def step_e2e(i):
+        cur, src = host_sets[i % n_sets]
+        cur_d = tree_map(lambda t: t.to(dev, non_blocking=True), cur)
+        src_d = tree_map(lambda t: t.to(dev, non_blocking=True), src)
+        out = model("test", cur_d, src_d, return_mask=True)
+        depth = out["depth_pred_s0_b1hw"]
+        if world > 1:
+            depth = sharding.gather_depth_maps(depth, frames_per_step)
+        host_out.copy_(depth[: cfg.batch], non_blocking=True)
+        return depth
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (compiles the conv plan, packs weights)
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+        step_e2e(i)
+    barrier()
+
+    # ---- device-timed region: one event pair per step, L2 flushed between steps outside the timed intervals
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record()
+        step_resident(i)
+        ends[i].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = L.launch_count() - launches0
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    dev_ms = reduce_max(dev_ms)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end region: host buffers -> public API -> host result, wall clock between device syncs
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    barrier()
+    e2e_s = reduce_max(time.perf_counter() - t0)
+
+    # ---- per-kernel timing for the roofline (rank 0, N=1 semantics): cost-volume kernel and the conv plan, alone
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        roof = kernel_rooflines(model, dev_sets, cfg, flush, L)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_base = cpu_baseline(cfg, budget_s=args.cpu_budget)
+
+    if rank == 0:
+        ms_per_step = dev_ms / args.steps
+        value = frames_per_step / (ms_per_step / 1e3)
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: DoubleTake 640x480 image, 120x160x16 matching feats, 64 planes, 7 src views, "
+                                   "rendered-depth hint on, batch 1 per GPU, CVEncoder+DepthDecoderPP (effnetv2-s priors)",
+                       "math": args.math, "frames_per_step": frames_per_step,
+                       "l2": "256 MiB L2 flush between timed steps (outside the per-step event pairs); 4 rotating input sets",
+                       "weights": "random-init (seeded), reference architecture",
+                       "wall_ms_per_step_incl_flush": round(1e3 * t_wall / args.steps, 4)},
+            "e2e": {"value": round(frames_per_step * args.steps / e2e_s, 3), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": host_out.numel() * 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof["dominant"] if roof else None,
+            "roofline_kernels": roof["all"] if roof else None,
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_rooflines(model, dev_sets, cfg, flush, L, reps=5):
+    """Live CUDA-event timing of the two kernel families on the launching stream (torch's current stream)."""
+    peaks = measured_peaks()
+    cur, src = dev_sets[0]
+    dev = flush.device
+    ext, pose = model._relative_poses(cur, src, dev)
+    mn = torch.tensor(model.run_opts.min_matching_depth).view(1, 1, 1, 1)
+    mx = torch.tensor(model.run_opts.max_matching_depth).view(1, 1, 1, 1)
+
+    def time_fn(fn):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        return sum(ts) / len(ts)
+
+    cv = {}
+
+    def run_cv():
+        cv["out"] = model.cost_volume._run(cur["matching_feats_bchw"], src["matching_feats_bkchw"], ext, pose,
+                                           src["K_s1_b44"], cur["invK_s1_b44"], mn, mx, cur, None, True)
+
+    cv_ms = time_fn(run_cv)
+    plan = model._network_plan(cv["out"]["volume"].shape, cur["image_prior_feats"])
+    conv_ms = time_fn(plan.run)
+    n_conv = len(plan.ops)
+    conv_flops = plan.flops()
+    cv_bytes = algorithmic_bytes_cost_volume(cfg, hint=True)
+    cv_flops = mlp_flops(cfg)
+    tens_peak = peaks["tf_sustained"]
+    entries = {
+        "cost_volume_mlp_hint": {
+            "bound": "tensor", "achieved": round(cv_flops / (cv_ms * 1e-3) / 1e12, 3), "peak": tens_peak, "unit": "TFLOP/s",
+            "frac": round(cv_flops / (cv_ms * 1e-3) / 1e12 / tens_peak, 5), "traffic": None,
+            "ms_per_launch": round(cv_ms, 4), "launches_per_step": 2,
+            "hbm_view": {"bound": "hbm", "achieved": round(cv_bytes / (cv_ms * 1e-3) / 1e9, 2), "peak": peaks["hbm"],
+                         "unit": "GB/s", "frac": round(cv_bytes / (cv_ms * 1e-3) / 1e9 / peaks["hbm"], 5),
+                         "algorithmic_bytes": cv_bytes},
+            "algorithmic_flops": cv_flops, "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a step)"},
+        "conv_stack": {
+            "bound": "tensor", "achieved": round(conv_flops / (conv_ms * 1e-3) / 1e12, 3), "peak": tens_peak,
+            "unit": "TFLOP/s", "frac": round(conv_flops / (conv_ms * 1e-3) / 1e12 / tens_peak, 5), "traffic": None,
+            "ms_per_launch": round(conv_ms / n_conv, 5), "launches_per_step": n_conv, "ms_all_launches": round(conv_ms, 4),
+            "algorithmic_flops": conv_flops, "peak_source": peaks["src"] + " bf16 sustained"},
+    }
+    dom = "conv_stack" if conv_ms >= cv_ms else "cost_volume_mlp_hint"
+    d = dict(entries[dom])
+    d["kernel"] = dom
+    return {"dominant": d, "all": entries}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's path on the host cores
+# --------------------------------------------------------------------------------------------------------------
+def cpu_sample_config(width_div):
+    c = syn.CONFIGS[WORKLOAD]
+    return syn.WorkloadConfig(f"cfg2_w{width_div}", c.batch, c.num_src, c.image_h, c.image_w // width_div, c.planes,
+                              hint=True, prior_ch=c.prior_ch, decoder=c.decoder, seed=c.seed)
+
+
+def cpu_step_fn(cfg_s):
+    """One pass of the reference algorithm (oracle port) over a 1/width_div-width crop of the cfg-2 frame: identical
+    per-pixel work (64 planes, 7 views, full conv stack), fewer pixels."""
+    from oracle import oracle_torch as orc
+    import doubletake_b200 as dt
+
+    inp = syn.cost_volume_inputs(cfg_s)
+    priors = syn.prior_features(cfg_s)
+    opts = dt.HotPathOptions(matching_num_depth_bins=cfg_s.planes, model_num_views=cfg_s.num_src + 1,
+                             image_height=cfg_s.image_h, image_width=cfg_s.image_w)
+    shapes = {k: tuple(v.shape) for k, v in dt.DepthModelCVHint(opts).named_parameters()}
+    w = syn.seeded_state_dict(shapes, 2024, 1.3)
+    eye = torch.eye(4).expand(cfg_s.batch, 4, 4).contiguous()
+    cur = {"cam_T_world_b44": eye, "world_T_cam_b44": eye, "invK_s1_b44": inp["cur_invK"], **inp["cv_depth_hint_dict"]}
+    src = {"cam_T_world_b44": inp["src_extrinsics"], "world_T_cam_b44": inp["src_poses"], "K_s1_b44": inp["src_Ks"]}
+
+    def step():
+        return orc.depth_model_forward(inp["cur_feats"], inp["src_feats"], priors, cur, src, w, cfg_s.planes, hint=True)
+
+    return step
+
+
+def pick_cpu_sample(total_steps, budget_s):
+    """Probe a 1/10-width crop, then choose the largest crop (width stays a multiple of 32) whose total run fits
+    the budget."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    probe = cpu_step_fn(cpu_sample_config(10))
+    probe()
+    t0 = time.perf_counter()
+    probe()
+    t10 = time.perf_counter() - t0
+    for div in (1, 2, 4, 10, 20):
+        if t10 * (10 / div) * total_steps <= budget_s or div == 20:
+            return div, cores
+
+
+def cpu_baseline(cfg, budget_s=25.0):
+    torch.set_grad_enabled(False)
+    div, cores = pick_cpu_sample(2, budget_s)
+    step = cpu_step_fn(cpu_sample_config(div))
+    step()
+    t0 = time.perf_counter()
+    step()
+    dt_s = time.perf_counter() - t0
+    return {"value": round((1.0 / div) / dt_s, 5), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle (torch CPU restatement of the reference path), 1 warm-up + 1 timed pass over a 1/{div}-width "
+                      f"crop of the cfg-2 frame (480x{640 // div} image, 64 planes, 7 views, hint, full conv stack) = "
+                      f"{1.0 / div:.3f} frame in {dt_s:.2f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    torch.set_grad_enabled(False)
+    warm = max(args.warmup, 1)
+    div, cores = pick_cpu_sample(args.steps + warm, args.ref_budget)
+    step = cpu_step_fn(cpu_sample_config(div))
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt_s = time.perf_counter() - t0
+    value = args.steps * (1.0 / div) / dt_s
+    sample = (f"each step = oracle port of the reference path over a 1/{div}-width crop of the cfg-2 frame "
+              f"(480x{640 // div} image, 64 planes, 7 views, hint, full conv stack) = {1.0 / div:.3f} frame")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": round(1e3 * dt_s / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2 (CPU arm: reference algorithm, torch CPU ops, all host threads)", "sample": sample},
+        "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--math", default="exact", choices=["exact", "tc3x"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--ref-budget", type=float, default=150.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

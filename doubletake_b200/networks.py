@@ -1,0 +1,384 @@
+"""B200 drop-ins for the reference's cost-volume encoder and depth decoders.
+
+``CVEncoder`` (reference modules/networks.py:88-117), ``DepthDecoderPP`` (modules/networks.py:20-85),
+``SkipDecoderRegression`` (modules/networks_fast.py:98-141) and ``BasicBlock`` (modules/layers.py:33-94) keep the
+reference's constructor arguments, ``forward`` signatures (NCHW tensors in and out) and ``state_dict`` keys, so
+checkpoints load unchanged and the modules are swapped in as ``model.cost_volume_net`` / ``model.depth_decoder``.
+
+The modules only HOLD parameters.  ``forward`` compiles, once per input shape, a ``ConvPlan`` -- an array of fused
+convolution descriptors (include/doubletake_b200.h: ``dtb200_conv_params``) over channels-last buffers in which
+``torch.cat``, the x2 up-samples, bias, residual add and activation are folded into the convolutions -- and replays
+it through ONE native call (``dtb200_conv2d_sequence``).  No PyTorch op touches an activation; no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# plan builder
+# ----------------------------------------------------------------------------------------------------------------
+class Feature:
+    """A channels-last activation buffer (B,H,W,C) inside a plan."""
+
+    __slots__ = ("t", "b", "h", "w", "c")
+
+    def __init__(self, t):
+        self.t = t
+        self.b, self.h, self.w, self.c = t.shape
+
+
+class ConvPlan:
+    """Records fused-conv descriptors over pre-allocated NHWC buffers; ``run()`` launches them from native code."""
+
+    def __init__(self, device, math="exact"):
+        self.device = device
+        self.math = L.MATH_NAMES[math]
+        self.ops = []
+        self.keep = []  # tensors referenced by raw pointers
+        self.inputs = {}  # name -> Feature filled from an NCHW tensor before run()
+        self._packed = {}
+        self._array = None
+
+    def new(self, b, h, w, c):
+        t = torch.empty((b, h, w, c), dtype=torch.float32, device=self.device)
+        self.keep.append(t)
+        return Feature(t)
+
+    def input(self, name, b, c, h, w):
+        f = self.new(b, h, w, c)
+        self.inputs[name] = f
+        return f
+
+    def _pack(self, weight):
+        key = id(weight)
+        if key not in self._packed:
+            w = L.f32(weight.detach(), self.device)
+            oc, ic, k, _ = w.shape
+            n = int(L.lib().dtb200_packed_conv_weight_floats(self.math, oc, ic, k))
+            packed = torch.empty(n, dtype=torch.float32, device=self.device)
+            L.check(L.lib().dtb200_pack_conv_weight(self.math, L.ptr(w), L.ptr(packed), oc, ic, k, L.stream()))
+            self._packed[key] = packed
+            self.keep.append(packed)
+        return self._packed[key]
+
+    def conv(self, srcs, conv: nn.Conv2d, act=L.ACT_NONE, slope=0.0, residual=None):
+        """srcs: list of (Feature, resample).  Returns the output Feature."""
+        k = conv.kernel_size[0]
+        stride = conv.stride[0]
+        f0, r0 = srcs[0]
+        in_h = f0.h * (2 if r0 != L.RESAMPLE_NONE else 1)
+        in_w = f0.w * (2 if r0 != L.RESAMPLE_NONE else 1)
+        pad = k // 2
+        out_h = (in_h + 2 * pad - k) // stride + 1
+        out_w = (in_w + 2 * pad - k) // stride + 1
+        total_c = 0
+        op = L.ConvParams()
+        op.math, op.batch = self.math, f0.b
+        op.in_h, op.in_w, op.out_h, op.out_w, op.out_c = in_h, in_w, out_h, out_w, conv.out_channels
+        op.ksize, op.stride, op.num_src = k, stride, len(srcs)
+        for i, (f, r) in enumerate(srcs):
+            fh = f.h * (2 if r != L.RESAMPLE_NONE else 1)
+            fw = f.w * (2 if r != L.RESAMPLE_NONE else 1)
+            if (fh, fw) != (in_h, in_w) or f.b != f0.b:
+                raise ValueError(f"concat sources disagree on shape: {(fh, fw)} vs {(in_h, in_w)}")
+            op.src[i], op.src_c[i], op.src_resample[i] = L.ptr(f.t), f.c, r
+            total_c += f.c
+        if total_c != conv.in_channels:
+            raise ValueError(f"conv expects {conv.in_channels} input channels, sources provide {total_c}")
+        op.weight = L.ptr(self._pack(conv.weight))
+        if conv.bias is not None:
+            bias = L.f32(conv.bias.detach(), self.device)
+            self.keep.append(bias)
+            op.bias = L.ptr(bias)
+        out = self.new(f0.b, out_h, out_w, conv.out_channels)
+        if residual is not None:
+            if (residual.b, residual.h, residual.w, residual.c) != (out.b, out.h, out.w, out.c):
+                raise ValueError("residual shape mismatch")
+            op.residual = L.ptr(residual.t)
+        op.act, op.act_slope = act, slope
+        op.dst = L.ptr(out.t)
+        self.ops.append(op)
+        return out
+
+    def finalize(self):
+        self._array = (L.ConvParams * len(self.ops))(*self.ops)
+        return self
+
+    def flops(self):
+        total = 0
+        for op in self.ops:
+            cin = sum(op.src_c[i] for i in range(op.num_src))
+            total += 2 * op.batch * op.out_h * op.out_w * op.out_c * cin * op.ksize * op.ksize
+        return total
+
+    def load_inputs(self, tensors: dict):
+        for name, x in tensors.items():
+            f = self.inputs[name]
+            if tuple(x.shape) != (f.b, f.c, f.h, f.w):
+                raise ValueError(f"plan input {name}: expected {(f.b, f.c, f.h, f.w)}, got {tuple(x.shape)}")
+            if not x.is_cuda:
+                raise RuntimeError("doubletake_b200 networks run on CUDA only (no CPU fallback)")
+            L.nchw_to_nhwc(x, out=f.t)
+
+    def run(self):
+        L.check(L.lib().dtb200_conv2d_sequence(self._array, len(self.ops), L.stream()))
+
+
+def _nchw_out(f: Feature):
+    """Plan output -> fresh NCHW tensor (1-channel maps are a pure reshape)."""
+    if f.c == 1:
+        return f.t.reshape(f.b, 1, f.h, f.w).clone()
+    return L.nhwc_to_nchw(f.t)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parameter-holding mirrors of the reference modules
+# ----------------------------------------------------------------------------------------------------------------
+class BasicBlock(nn.Module):
+    """reference modules/layers.py:33-94 with norm_layer=Identity (bias on every conv, LeakyReLU(0.2), optional
+    1x1 / strided-3x3 projection on the skip).  Keys: conv1, conv2, downsample.0."""
+
+    def __init__(self, inplanes, planes, stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride=stride, padding=1, bias=True)
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=True)
+        if inplanes == planes and stride == 1:
+            self.downsample = None
+        else:
+            k = 1 if stride == 1 else 3
+            self.downsample = nn.Sequential(nn.Conv2d(inplanes, planes, k, stride=stride, padding=k // 2, bias=True),
+                                            nn.Identity())
+        self.stride = stride
+
+    def emit(self, plan: ConvPlan, srcs):
+        """layers.py:77-94 as 2-3 fused convs: t = lrelu(conv1(x)); out = lrelu(conv2(t) + (x | proj(x)))."""
+        t = plan.conv(srcs, self.conv1, L.ACT_LEAKY, 0.2)
+        if self.downsample is not None:
+            skip = plan.conv(srcs, self.downsample[0])
+        else:
+            if len(srcs) != 1 or srcs[0][1] != L.RESAMPLE_NONE:
+                raise ValueError("identity skip needs a single, non-resampled source")
+            skip = srcs[0][0]
+        return plan.conv([(t, L.RESAMPLE_NONE)], self.conv2, L.ACT_LEAKY, 0.2, residual=skip)
+
+    def forward(self, x):
+        raise RuntimeError("doubletake_b200.BasicBlock is executed through its parent's ConvPlan")
+
+
+class _PlannedModule(nn.Module):
+    """Caches compiled plans per (input shapes, device); invalidated when parameters are reloaded or moved."""
+
+    def __init__(self, math="exact"):
+        super().__init__()
+        self.math = math
+        self._plans = {}
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._plans.clear())
+
+    def _apply(self, fn, recurse=True):
+        self._plans = {}
+        return super()._apply(fn, recurse)
+
+    def set_math(self, math):
+        self.math = math
+        self._plans = {}
+        return self
+
+    def _plan_for(self, key, build):
+        key = (key, self.math)
+        if key not in self._plans:
+            self._plans[key] = build()
+        return self._plans[key]
+
+
+class CVEncoder(_PlannedModule):
+    """reference modules/networks.py:88-117."""
+
+    def __init__(self, num_ch_cv, num_ch_enc, num_ch_outs, math="exact"):
+        super().__init__(math)
+        self.convs = nn.ModuleDict()
+        self.num_ch_enc = []
+        self.num_blocks = len(num_ch_outs)
+        for i in range(self.num_blocks):
+            cin = num_ch_cv if i == 0 else num_ch_outs[i - 1]
+            cout = num_ch_outs[i]
+            self.convs[f"ds_conv_{i}"] = BasicBlock(cin, cout, stride=1 if i == 0 else 2)
+            self.convs[f"conv_{i}"] = nn.Sequential(BasicBlock(num_ch_enc[i] + cout, cout), BasicBlock(cout, cout))
+            self.num_ch_enc.append(cout)
+
+    def emit(self, plan, x: Feature, img_feats):
+        outs = []
+        for i in range(self.num_blocks):
+            x = self.convs[f"ds_conv_{i}"].emit(plan, [(x, L.RESAMPLE_NONE)])
+            # torch.cat([x, img_feats[i]]) (networks.py:114) is folded into the next block's loaders
+            x = self.convs[f"conv_{i}"][0].emit(plan, [(x, L.RESAMPLE_NONE), (img_feats[i], L.RESAMPLE_NONE)])
+            x = self.convs[f"conv_{i}"][1].emit(plan, [(x, L.RESAMPLE_NONE)])
+            outs.append(x)
+        return outs
+
+    def forward(self, x, img_feats):
+        shapes = (tuple(x.shape),) + tuple(tuple(f.shape) for f in img_feats)
+
+        def build():
+            plan = ConvPlan(x.device, self.math)
+            fx = plan.input("x", *x.shape)
+            fi = [plan.input(f"img{i}", *f.shape) for i, f in enumerate(img_feats)]
+            plan.outputs = self.emit(plan, fx, fi)
+            return plan.finalize()
+
+        plan = self._plan_for((shapes, str(x.device)), build)
+        plan.load_inputs({"x": x, **{f"img{i}": f for i, f in enumerate(img_feats)}})
+        plan.run()
+        return [_nchw_out(f) for f in plan.outputs]
+
+
+def _double_basic_block(cin, cout):
+    layers = nn.Sequential(BasicBlock(cin, cout))
+    layers.add_module("conv_0", BasicBlock(cout, cout))  # key name of the reference (networks.py:13-17)
+    return layers
+
+
+class DepthDecoderPP(_PlannedModule):
+    """reference modules/networks.py:20-85 (UNet++ decoder, 4 log-depth heads)."""
+
+    def __init__(self, num_ch_enc, scales=range(4), num_output_channels=1, use_skips=True, math="exact"):
+        super().__init__(math)
+        self.num_output_channels = num_output_channels
+        self.num_ch_enc = list(num_ch_enc)
+        self.num_ch_dec = np.array([64, 64, 128, 256])
+        self.convs = nn.ModuleDict()
+        for j in range(1, 5):
+            for i in range(4 - j, -1, -1):
+                cout = int(self.num_ch_dec[i])
+                total = 0
+                cin = self.num_ch_enc[i + 1] if j == 1 else int(self.num_ch_dec[i + 1])
+                self.convs[f"diag_conv_{i + 1}{j - 1}"] = BasicBlock(cin, cout)
+                total += cout
+                cin = self.num_ch_enc[i] if j == 1 else int(self.num_ch_dec[i])
+                self.convs[f"right_conv_{i}{j - 1}"] = BasicBlock(cin, cout)
+                total += cout
+                if i + j != 4:
+                    self.convs[f"up_conv_{i + 1}{j}"] = BasicBlock(int(self.num_ch_dec[i + 1]), cout)
+                    total += cout
+                self.convs[f"in_conv_{i}{j}"] = _double_basic_block(total, cout)
+                self.convs[f"output_{i}"] = nn.Sequential(
+                    BasicBlock(cout, cout) if i != 0 else nn.Identity(), nn.Conv2d(cout, num_output_channels, 1))
+
+    def emit(self, plan, feats):
+        """networks.py:65-85.  ``upsample`` (bilinear x2) and ``torch.cat`` are folded into in_conv's loaders; only the
+        head evaluation that survives per scale (last write to the dict key, networks.py:81) is emitted."""
+        prev = list(feats)
+        heads = {}
+        UP = L.RESAMPLE_BILINEAR_UP2
+        for j in range(1, 5):
+            col = []
+            for i in range(4 - j, -1, -1):
+                parts = [(self.convs[f"right_conv_{i}{j - 1}"].emit(plan, [(prev[i], L.RESAMPLE_NONE)]), L.RESAMPLE_NONE)]
+                parts.append((self.convs[f"diag_conv_{i + 1}{j - 1}"].emit(plan, [(prev[i + 1], L.RESAMPLE_NONE)]), UP))
+                if i + j != 4:
+                    parts.append((self.convs[f"up_conv_{i + 1}{j}"].emit(plan, [(col[-1], L.RESAMPLE_NONE)]), UP))
+                block = self.convs[f"in_conv_{i}{j}"]
+                x = block[0].emit(plan, parts)
+                x = block.conv_0.emit(plan, [(x, L.RESAMPLE_NONE)])
+                col.append(x)
+                if i + j == 4:
+                    head = self.convs[f"output_{i}"]
+                    h = x
+                    if i != 0:
+                        h = head[0].emit(plan, [(h, L.RESAMPLE_NONE)])
+                    heads[f"log_depth_pred_s{i}_b1hw"] = plan.conv([(h, L.RESAMPLE_NONE)], head[1])
+            prev = col[::-1]
+        return heads
+
+    def forward(self, input_features):
+        shapes = tuple(tuple(f.shape) for f in input_features)
+        dev = input_features[0].device
+
+        def build():
+            plan = ConvPlan(dev, self.math)
+            fi = [plan.input(f"f{i}", *f.shape) for i, f in enumerate(input_features)]
+            plan.outputs = self.emit(plan, fi)
+            return plan.finalize()
+
+        plan = self._plan_for((shapes, str(dev)), build)
+        plan.load_inputs({f"f{i}": f for i, f in enumerate(input_features)})
+        plan.run()
+        return {k: _nchw_out(v) for k, v in sorted(plan.outputs.items(), reverse=True)}
+
+
+class ConvBlock(nn.Module):
+    """reference modules/networks_fast.py:6-27 (two 3x3 convs, ELU)."""
+
+    def __init__(self, in_ch, out_ch):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_ch, out_ch, 3, padding=1)
+        self.conv2 = nn.Conv2d(out_ch, out_ch, 3, padding=1)
+
+    def emit(self, plan, srcs):
+        x = plan.conv(srcs, self.conv1, L.ACT_ELU)
+        return plan.conv([(x, L.RESAMPLE_NONE)], self.conv2, L.ACT_ELU)
+
+
+class ConvUpsampleAndConcatBlock(nn.Module):
+    """reference modules/networks_fast.py:29-44."""
+
+    def __init__(self, in_ch, out_ch, skip_chns):
+        super().__init__()
+        self.pre_concat_conv = ConvBlock(in_ch, out_ch)
+        self.post_concat_conv = ConvBlock(out_ch + skip_chns, out_ch)
+
+    def emit(self, plan, x, skip):
+        x = self.pre_concat_conv.emit(plan, [(x, L.RESAMPLE_NONE)])
+        # F.interpolate(nearest x2) + torch.cat (networks_fast.py:38-39) folded into the loader
+        return self.post_concat_conv.emit(plan, [(x, L.RESAMPLE_NEAREST_UP2), (skip, L.RESAMPLE_NONE)])
+
+
+class SkipDecoderRegression(_PlannedModule):
+    """reference modules/networks_fast.py:47-141 (SkipDecoder + 1x1-conv regression heads)."""
+
+    def __init__(self, input_channels, use_bn=False, math="exact"):
+        super().__init__(math)
+        ic = list(input_channels)[::-1]
+        self.input_channels = ic
+        self.output_channels = [256, 128, 64, 64]
+        self.num_ch_dec = self.output_channels[::-1]
+        for n in range(4):
+            setattr(self, f"block{n + 1}", ConvUpsampleAndConcatBlock(ic[n], self.output_channels[n], ic[n + 1]))
+        for n in range(4):
+            setattr(self, f"out{n + 1}", nn.Sequential(
+                nn.Conv2d(self.output_channels[n], 128, 1), nn.ELU(inplace=True), nn.Conv2d(128, 128, 1),
+                nn.ELU(inplace=True), nn.Conv2d(128, 1, 1)))
+
+    def emit(self, plan, feats):
+        outs = {}
+        x = feats[-1]
+        for n in range(1, 5):
+            x = getattr(self, f"block{n}").emit(plan, x, feats[-1 - n])
+            s = 4 - n
+            outs[f"feature_s{s}_b1hw"] = x
+            head = getattr(self, f"out{n}")
+            h = plan.conv([(x, L.RESAMPLE_NONE)], head[0], L.ACT_ELU)
+            h = plan.conv([(h, L.RESAMPLE_NONE)], head[2], L.ACT_ELU)
+            outs[f"log_depth_pred_s{s}_b1hw"] = plan.conv([(h, L.RESAMPLE_NONE)], head[4])
+        return outs
+
+    def forward(self, features):
+        shapes = tuple(tuple(f.shape) for f in features)
+        dev = features[0].device
+
+        def build():
+            plan = ConvPlan(dev, self.math)
+            fi = [plan.input(f"f{i}", *f.shape) for i, f in enumerate(features)]
+            plan.outputs = self.emit(plan, fi)
+            return plan.finalize()
+
+        plan = self._plan_for((shapes, str(dev)), build)
+        plan.load_inputs({f"f{i}": f for i, f in enumerate(features)})
+        plan.run()
+        return {k: _nchw_out(v) for k, v in plan.outputs.items()}

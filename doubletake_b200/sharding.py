@@ -1,0 +1,56 @@
+"""Frame-level data parallelism for inference.
+
+Reference keyframes are independent units (each frame's cost volume + decoder touches only its own K source views;
+the reference itself runs inference on one GPU: README.md:125,307,326,344).  One process per GPU: global frame ``i``
+goes to rank ``i % world_size``; every rank holds a full weight replica; the ONLY exchange is one gather of the
+predicted depth maps per step (``all_gather`` over NCCL on NVLink; ``gloo`` on CPU for the host-logic tests).
+Incremental mode is sequential inside a scan, so there the unit is the scan (``shard_scans``).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_frames(num_frames: int, rank: int, world_size: int):
+    """Indices of the frames this rank owns: round-robin, as cfg 4 of BASELINE.json asks."""
+    return list(range(rank, num_frames, world_size))
+
+
+def shard_scans(scan_lengths, rank: int, world_size: int):
+    """Greedy longest-first assignment of whole scans to ranks (incremental mode: a frame's hint depends on the
+    fused depths of the earlier frames of its scan, reference test_incremental.py:186-269)."""
+    order = sorted(range(len(scan_lengths)), key=lambda i: -scan_lengths[i])
+    load = [0] * world_size
+    mine = []
+    for i in order:
+        r = min(range(world_size), key=lambda j: (load[j], j))
+        load[r] += scan_lengths[i]
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
+
+
+def gather_depth_maps(local_depth: torch.Tensor, num_frames: int, group=None):
+    """Gather per-rank depth maps (n_local,1,H,W) into frame order (num_frames,1,H,W) on every rank.
+
+    Ranks may own ceil or floor(num_frames / world) frames; shorter shards are zero-padded for the collective and
+    trimmed afterwards.  This is the path's single collective."""
+    if not dist.is_available() or not dist.is_initialized():
+        return local_depth
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per = (num_frames + world - 1) // world
+    pad = per - local_depth.shape[0]
+    send = local_depth
+    if pad > 0:
+        send = torch.cat([local_depth, local_depth.new_zeros((pad,) + tuple(local_depth.shape[1:]))], 0)
+    send = send.contiguous()
+    recv = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+    dist.all_gather_into_tensor(recv.view(-1, *send.shape[1:]), send, group=group) if send.is_cuda else \
+        dist.all_gather(list(recv.unbind(0)), send, group=group)
+    out = local_depth.new_empty((num_frames,) + tuple(local_depth.shape[1:]))
+    for r in range(world):
+        idx = shard_frames(num_frames, r, world)
+        out[idx] = recv[r, : len(idx)]
+    return out

@@ -1,0 +1,165 @@
+/*
+ * doubletake_b200 -- C ABI of the B200-native plane-sweep MVS depth engine.
+ *
+ * The reference (nianticlabs/doubletake) has no FFI: its "plugin API" for this path is Python duck-typing on the
+ * nn.Module attributes of the LightningModule (model.cost_volume / model.cost_volume_net / model.depth_decoder,
+ * swapped the way utils/model_utils.py:30-34 swaps in the "fast" cost volume).  This header is the C boundary a
+ * maintainer binds underneath those attributes (ctypes stub in INTEGRATION.md).  Plain pointers and sizes only:
+ * no torch types, no allocation inside, no exceptions across the ABI.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 unless stated; all tensors dense/contiguous in the stated layout
+ *   - every entry point enqueues work on `stream` and returns immediately (0 = ok, <0 = error code below;
+ *     dtb200_last_error() gives the message for the calling thread)
+ *   - thread-safe per stream; no global mutable state besides the per-thread error string
+ */
+#ifndef DOUBLETAKE_B200_H
+#define DOUBLETAKE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dtb200_stream_t; /* cudaStream_t */
+
+#define DTB200_OK 0
+#define DTB200_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define DTB200_ERR_CUDA (-2)      /* CUDA runtime error on launch */
+#define DTB200_ERR_UNSUPPORTED (-3)
+
+#define DTB200_ABI_VERSION 1
+#define DTB200_MAX_VIEWS 16
+
+int dtb200_abi_version(void);
+const char* dtb200_last_error(void);
+/* number of kernels this library has launched from the calling process (bench.py's gpu_launches claim) */
+uint64_t dtb200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Layout helpers (boundary transposes; the reference hands NCHW tensors, the kernels gather channels-last)
+ * ---------------------------------------------------------------------------------------------------------- */
+int dtb200_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, dtb200_stream_t stream);
+int dtb200_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, dtb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Plane-sweep cost volumes.
+ *
+ * Replaces, in one launch per batch, the per-plane Python loop of
+ *   CostVolumeManager.build_cost_volume + forward          (modules/cost_volume.py:219-363)        kind = DOT
+ *   FeatureVolumeManager.build_cost_volume + forward       (modules/feature_volume.py:81-356)      kind = MLP
+ *   FeatureMeshHintVolumeManager.build_cost_volume+forward (modules/mesh_hint_volume.py:84-439)    kind = MLP_HINT
+ * i.e. BackprojectDepth/Project3D (utils/geometry_utils.py:55-93), F.grid_sample warp, dot product + mask,
+ * metadata assembly (26K+20 channels, order of mesh_hint_volume.py:343-367), MLP 26K+20 -> 128 -> 128 -> 1,
+ * hint MLP 3 -> 12 -> 12 -> 1, arg-max over planes -> lowest_cost depth, and the overall source-view mask.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define DTB200_VOLUME_DOT 0
+#define DTB200_VOLUME_MLP 1
+#define DTB200_VOLUME_MLP_HINT 2
+
+/* math modes: EXACT = fp32 FMA in the reference operation order (bit-reproducible, CUDA cores);
+ * TC3X = tcgen05 tensor cores with the 3xTF32 split (fp32-class accuracy, ~2^-21 per product) */
+#define DTB200_MATH_EXACT 0
+#define DTB200_MATH_TC3X 1
+
+typedef struct {
+  int32_t kind;          /* DTB200_VOLUME_* */
+  int32_t math;          /* DTB200_MATH_* (DOT ignores it) */
+  int32_t batch, views, channels, height, width, planes; /* B K C H W D ; C must be 16 */
+  /* inputs */
+  const float* cur_feats;       /* (B,C,H,W)   NCHW, as the reference passes it */
+  const float* src_feats_nhwc;  /* (B,K,H,W,C) channels-last staging of the reference's (B,K,C,H,W) */
+  const float* src_extrinsics;  /* (B,K,4,4) src_cam_T_cur_cam, row-major */
+  const float* src_poses;       /* (B,K,4,4) cur_cam_T_src_cam */
+  const float* src_Ks;          /* (B,K,4,4) intrinsics at matching resolution */
+  const float* cur_invK;        /* (B,4,4) */
+  const float* plane_depths;    /* (B,D) plane depths, or (B,D,H,W) when planes_per_pixel != 0 */
+  int32_t planes_per_pixel;
+  /* hint branch (MLP_HINT only): maps at hint_height x hint_width, nearest-resampled to HxW in-kernel
+   * (mesh_hint_volume.py:186-204).  depth_hint may hold NaN where hint_mask == 0. */
+  const float* depth_hint;      /* (B,1,Hh,Wh) */
+  const float* hint_weights;    /* (B,1,Hh,Wh) */
+  const float* hint_mask;       /* (B,1,Hh,Wh) float 0/1 */
+  int32_t hint_height, hint_width;
+  /* weights, PyTorch Linear layout (out,in) row-major: keys mlp.net.{0,2,4}, hint_mlp.net.{0,2,4} */
+  const float* w1; const float* b1;   /* (128, 26K+20), (128) */
+  const float* w2; const float* b2;   /* (128,128), (128) */
+  const float* w3; const float* b3;   /* (1,128), (1) */
+  const float* hw1; const float* hb1; /* (12,3), (12) */
+  const float* hw2; const float* hb2; /* (12,12), (12) */
+  const float* hw3; const float* hb3; /* (1,12), (1) */
+  /* outputs */
+  float* volume;        /* (B,D,H,W) */
+  float* lowest_cost;   /* (B,H,W) plane depth at arg-max (first max wins); may be NULL */
+  int32_t* best_index;  /* (B,H,W) arg-max plane index; may be NULL */
+  uint8_t* mask_views;  /* (B,K,H,W) last-plane depth-valid & in-bounds per view; may be NULL */
+  uint8_t* mask_any;    /* (B,H,W) any_k(depth-valid) & any_k(in-bounds) on the last plane; may be NULL */
+  /* scratch for math = TC3X (see dtb200_cost_volume_workspace_bytes); may be NULL otherwise */
+  void* workspace;
+  uint64_t workspace_bytes;
+} dtb200_cost_volume_params;
+
+uint64_t dtb200_cost_volume_workspace_bytes(const dtb200_cost_volume_params* p);
+int dtb200_cost_volume(const dtb200_cost_volume_params* p, dtb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused 2-D convolution, channels-last.  One descriptor covers every conv of
+ *   BasicBlock (modules/layers.py:33-94), CVEncoder (modules/networks.py:88-117),
+ *   DepthDecoderPP (modules/networks.py:20-85) and SkipDecoderRegression (modules/networks_fast.py:6-141):
+ *     out = act( conv_{k x k, stride}( concat_c[ resample_i(src_i) ] ) + bias (+ residual) )
+ * with torch.cat (networks.py:78,114; networks_fast.py:39) and the x2 upsamples (bilinear align_corners=False,
+ * utils/generic_utils.py:95-104; nearest, networks_fast.py:38) applied on load, never materialised.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define DTB200_RESAMPLE_NONE 0
+#define DTB200_RESAMPLE_BILINEAR_UP2 1
+#define DTB200_RESAMPLE_NEAREST_UP2 2
+
+#define DTB200_ACT_NONE 0
+#define DTB200_ACT_LEAKY 1 /* slope in act_slope */
+#define DTB200_ACT_ELU 2   /* alpha = 1 */
+
+#define DTB200_CONV_MAX_SRC 3
+
+typedef struct {
+  int32_t math;                 /* DTB200_MATH_* */
+  int32_t batch;
+  int32_t in_h, in_w;           /* conv-input spatial size (after resampling): out = floor((in + 2*pad - k)/stride) + 1 */
+  int32_t out_h, out_w, out_c;  /* output spatial size and channels */
+  int32_t ksize, stride;        /* 3 (pad 1) or 1 (pad 0); stride 1 or 2 */
+  int32_t num_src;
+  const float* src[DTB200_CONV_MAX_SRC];      /* NHWC; spatial = conv-input size, or half of it when upsampled */
+  int32_t src_c[DTB200_CONV_MAX_SRC];
+  int32_t src_resample[DTB200_CONV_MAX_SRC];  /* DTB200_RESAMPLE_* */
+  const float* weight;   /* packed by dtb200_pack_conv_weight for `math` */
+  const float* bias;     /* (out_c) or NULL */
+  const float* residual; /* NHWC (B,out_h,out_w,out_c) added before the activation, or NULL */
+  int32_t act;
+  float act_slope;
+  float* dst;            /* NHWC (B,out_h,out_w,out_c) */
+} dtb200_conv_params;
+
+/* floats needed for the packed copy of an (out_c, in_c, k, k) OIHW weight */
+uint64_t dtb200_packed_conv_weight_floats(int32_t math, int32_t out_c, int32_t in_c, int32_t ksize);
+/* device->device repack of a PyTorch OIHW weight into the layout `math` consumes */
+int dtb200_pack_conv_weight(int32_t math, const float* oihw, float* packed, int32_t out_c, int32_t in_c,
+                            int32_t ksize, dtb200_stream_t stream);
+int dtb200_conv2d(const dtb200_conv_params* p, dtb200_stream_t stream);
+/* Launch a whole network (an array of conv descriptors, in order) from one native call. */
+int dtb200_conv2d_sequence(const dtb200_conv_params* ops, int32_t count, dtb200_stream_t stream);
+
+/* Relative camera poses of DepthModel.forward (experiment_modules/doubletake_model.py:341-349):
+ *   src_cam_T_cur_cam[b,k] = src_cam_T_world[b,k] @ cur_world_T_cam[b]   (the managers' src_extrinsics)
+ *   cur_cam_T_src_cam[b,k] = cur_cam_T_world[b] @ src_world_T_cam[b,k]   (the managers' src_poses)
+ * all row-major 4x4; src tensors (B,K,4,4), cur tensors (B,4,4). */
+int dtb200_relative_poses(const float* src_cam_T_world, const float* src_world_T_cam, const float* cur_cam_T_world,
+                          const float* cur_world_T_cam, float* src_cam_T_cur_cam, float* cur_cam_T_src_cam,
+                          int batch, int views, dtb200_stream_t stream);
+
+/* out = exp(in), elementwise (experiment_modules/doubletake_model.py:410-418) */
+int dtb200_exp(const float* src, float* dst, uint64_t count, dtb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOUBLETAKE_B200_H */

@@ -1,0 +1,103 @@
+"""GPU parity of the fused conv plans (CVEncoder, DepthDecoderPP, SkipDecoderRegression) through the C ABI."""
+import json
+
+import pytest
+import torch
+
+import helpers as hp
+import doubletake_b200 as dt
+from doubletake_b200 import _lib as L
+from doubletake_b200 import synthetic as syn
+from oracle import oracle_torch as orc
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+DEV = "cuda"
+
+
+def build(fx, decoder, D, prior_ch, seed, math="exact"):
+    enc = dt.CVEncoder(D, list(prior_ch[1:]), [64, 128, 256, 384], math=math)
+    dec_in = list(prior_ch[:1]) + enc.num_ch_enc
+    dec = (dt.DepthDecoderPP(dec_in, math=math) if decoder == "unet_pp" else dt.SkipDecoderRegression(dec_in, math=math))
+    encw = syn.seeded_state_dict(json.loads(str(fx["enc_shapes"])), seed + 1, 1.5)
+    decw = syn.seeded_state_dict(json.loads(str(fx["dec_shapes"])), seed + 2, 1.5)
+    enc.load_state_dict(encw)
+    dec.load_state_dict(decw)
+    return enc.to(DEV), dec.to(DEV), encw, decw
+
+
+@pytest.mark.parametrize("name,decoder", [("net_pp_d64", "unet_pp"), ("net_pp_d16_b2", "unet_pp"),
+                                           ("net_skip_d48", "skip")])
+def test_conv_stacks_match_reference_fixture(name, decoder):
+    fx = hp.load(name)
+    cfg, cv, priors, seed = hp.network_case_inputs(fx, decoder)
+    enc, dec, _, _ = build(fx, decoder, cfg.planes, cfg.prior_ch, seed)
+    cvf = enc(cv.to(DEV), [p.to(DEV) for p in priors[1:]])
+    for i, f in enumerate(cvf):
+        assert f.shape == fx[f"out.cv_feat_{i}"].shape
+        assert hp.rel_err(f.cpu(), fx[f"out.cv_feat_{i}"]) < 1e-5
+    out = dec([priors[0].to(DEV)] + cvf)
+    for i in range(4):
+        k = f"log_depth_pred_s{i}_b1hw"
+        ref = torch.from_numpy(fx["out." + k])
+        assert out[k].shape == ref.shape
+        assert float((out[k].cpu() - ref).abs().max()) < 1e-4, k
+    if decoder == "skip":
+        assert hp.rel_err(out["feature_s3_b1hw"].cpu(), fx["out.feature_s3_b1hw"]) < 1e-5
+
+
+@pytest.mark.parametrize("ih,iw,B", [(96, 160, 1), (160, 96, 2)])
+def test_odd_sizes_against_oracle(ih, iw, B):
+    """Sizes whose /32 maps are odd (3x5, 5x3): partial 8x8 tiles, stride-2 convs on odd inputs."""
+    fx = hp.load("net_pp_d64")
+    prior_ch = (24, 48, 64, 160, 256)
+    cfg = syn.WorkloadConfig("t", B, 2, ih, iw, 64, prior_ch=prior_ch, seed=51)
+    priors = syn.prior_features(cfg)
+    cv = torch.randn(B, 64, ih // 4, iw // 4, generator=torch.Generator().manual_seed(3))
+    enc, dec, encw, decw = build(fx, "unet_pp", 64, prior_ch, 700)
+    cvf = enc(cv.to(DEV), [p.to(DEV) for p in priors[1:]])
+    out = dec([priors[0].to(DEV)] + cvf)
+    rcvf = orc.cv_encoder(cv, priors[1:], encw)
+    ref = orc.depth_decoder_pp(priors[:1] + rcvf, decw)
+    for i in range(4):
+        assert hp.rel_err(cvf[i].cpu(), rcvf[i]) < 1e-5
+        k = f"log_depth_pred_s{i}_b1hw"
+        assert float((out[k].cpu() - ref[k]).abs().max()) < 1e-4
+
+
+def test_single_conv_features_against_torch():
+    """Each fused feature of dtb200_conv2d in isolation: concat of 3 sources, bilinear / nearest x2 on load, stride 2,
+    1x1, residual, LeakyReLU / ELU -- against F.conv2d on CPU."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    B, H, W = 2, 10, 12
+    a = torch.randn(B, 16, H, W, generator=g)
+    b = torch.randn(B, 24, H // 2, W // 2, generator=g)
+    c = torch.randn(B, 8, H // 2, W // 2, generator=g)
+    res = torch.randn(B, 64, H, W, generator=g)
+    conv = nn.Conv2d(48, 64, 3, padding=1)
+    plan = dt.ConvPlan(torch.device(DEV), "exact")
+    fa, fb, fc = plan.input("a", *a.shape), plan.input("b", *b.shape), plan.input("c", *c.shape)
+    fr = plan.input("r", *res.shape)
+    o1 = plan.conv([(fa, L.RESAMPLE_NONE), (fb, L.RESAMPLE_BILINEAR_UP2), (fc, L.RESAMPLE_NEAREST_UP2)], conv,
+                   L.ACT_LEAKY, 0.2, residual=fr)
+    conv2 = nn.Conv2d(64, 128, 3, stride=2, padding=1)
+    o2 = plan.conv([(o1, L.RESAMPLE_NONE)], conv2, L.ACT_ELU)
+    conv3 = nn.Conv2d(128, 64, 1)
+    o3 = plan.conv([(o2, L.RESAMPLE_NONE)], conv3)
+    head = nn.Conv2d(64, 1, 1)
+    o4 = plan.conv([(o3, L.RESAMPLE_NONE)], head)
+    plan.finalize()
+    plan.load_inputs({"a": a.to(DEV), "b": b.to(DEV), "c": c.to(DEV), "r": res.to(DEV)})
+    plan.run()
+    x = torch.cat([a, F.interpolate(b, scale_factor=2, mode="bilinear", align_corners=False),
+                   F.interpolate(c, scale_factor=2, mode="nearest")], 1)
+    r1 = F.leaky_relu(conv(x) + res, 0.2)
+    r2 = F.elu(conv2(r1))
+    r3 = conv3(r2)
+    r4 = head(r3)
+    for o, r in ((o1, r1), (o2, r2), (o3, r3), (o4, r4)):
+        got = o.t.cpu().permute(0, 3, 1, 2)
+        assert got.shape == r.shape
+        assert hp.rel_err(got, r) < 1e-5
