@@ -387,13 +387,21 @@ def cpu_step_fn(cfg_s):
 def pick_cpu_sample(total_steps, budget_s):
     """Probe a 1/10-width crop, then choose the largest crop (width stays a multiple of 32) whose total run fits
     the budget."""
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     probe = cpu_step_fn(cpu_sample_config(10))
-    probe()
-    t0 = time.perf_counter()
-    probe()
-    t10 = time.perf_counter() - t0
+    # "all the host threads it can use": torch's CPU ops on this path stop scaling (and regress) well below the
+    # core count of the GPU hosts, so probe a few thread counts and keep the fastest
+    best = None
+    for n in sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
+        torch.set_num_threads(n)
+        probe()
+        t0 = time.perf_counter()
+        probe()
+        t = time.perf_counter() - t0
+        if best is None or t < best[0]:
+            best = (t, n)
+    t10, cores = best
+    torch.set_num_threads(cores)
     for div in (1, 2, 4, 10, 20):
         if t10 * (10 / div) * total_steps <= budget_s or div == 20:
             return div, cores
