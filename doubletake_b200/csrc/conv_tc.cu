@@ -1,14 +1,302 @@
-// tcgen05 (3xTF32) implicit-GEMM convolution -- placeholder until the tensor-core path lands.
+// Fused channels-last convolution on 5th-gen tensor cores (tcgen05, TMEM accumulators), math = TC3X, sm_100a.
+//
+//   dst = act( conv_{k x k, stride}( concat_c[ resample_i(src_i) ] ) + bias (+ residual) )
+//
+// Implicit GEMM per CTA: D[128 pixels x BN channels] += A[128 x K] * B[BN x K]^T with K = taps x concatenated input
+// channels, walked in blocks of 32 (4 groups of 8 channels; a group never straddles a source, so torch.cat is free).
+//
+// Precision: 3xTF32.  Every fp32 operand x is split into big = tf32-truncated x and small = x - big (both exact);
+// per K step three kind::tf32 MMAs accumulate small*big + big*small + big*big in fp32 TMEM.  Per-product error ~2^-21:
+// fp32-class, which the 1e-4 relative depth bar needs through ~20 stacked convs (plain TF32/BF16 does not meet it).
+//
+// Warp roles (288 threads):
+//   warps 0-7  producers: im2col gather (zero padding, concat, x2 up-sampling on load) -> split -> st.shared into the
+//              SWIZZLE_128B K-major A_big / A_small tiles; fence.proxy.async; one mbarrier arrival per warp.
+//              Afterwards the same warps run the epilogue: tcgen05.ld -> bias/residual/activation -> NHWC store.
+//   warp 8     lane 0: cp.async.bulk of the pre-swizzled, pre-split weight tile (UBLKCP, complete_tx on the same
+//              mbarrier), then tcgen05.mma issue (12 per K block) and tcgen05.commit to release the stage.
+// Weights are packed once (dtb200_pack_conv_weight) into the exact shared-memory image of each (N tile, K block).
 #include "common.cuh"
+#include "conv_common.cuh"
+#include "tc_common.cuh"
+
 namespace dtb200 {
-int launch_conv_tc(const dtb200_conv_params&, int, cudaStream_t) {
-  return fail(DTB200_ERR_UNSUPPORTED, "conv: math=TC3X not built yet%s");
+
+using namespace tc;
+
+constexpr int kBM = 128;                 // pixels per CTA tile (UMMA M)
+constexpr int kBK = 32;                  // fp32 per K block = one 128-byte swizzled row
+constexpr int kProducerWarps = 8;
+constexpr int kThreads = (kProducerWarps + 1) * 32;
+constexpr int kATileBytes = kBM * 128;   // 16 KB
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kBTileBytes = BN * 128;
+  static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;  // A_big, A_small, B_big, B_small
+  static constexpr int kStages = BN <= 64 ? 2 : 3;
+  static constexpr int kMinBlocks = BN <= 64 ? 2 : 1;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 2048 /*row info*/ + 256 /*barriers*/;
+};
+
+__host__ __device__ inline int tc_num_kblocks(int in_c, int ksize) { return (in_c * ksize * ksize + kBK - 1) / kBK; }
+__host__ __device__ inline int tc_bn(int out_c) { return (out_c % 128 == 0) ? 128 : 64; }
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, TcCfg<BN>::kMinBlocks) conv_tc_kernel(const dtb200_conv_params p, int in_c_total, long long m_total,
+                                                           int num_kb) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  int4* rowinfo = reinterpret_cast<int4*>(smem + Cfg::kStages * Cfg::kStageBytes);  // [128] {b, oy, ox, valid}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rowinfo) + 2048);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + Cfg::kStages;       // [kStages]
+  uint64_t* accum = bars + 2 * Cfg::kStages;   // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long m0 = (long long)blockIdx.x * kBM;
+  const int n_tile = blockIdx.y;
+
+  if (tid < kBM) {
+    long long m = m0 + tid;
+    int4 ri = make_int4(0, 0, 0, 0);
+    if (m < m_total) {
+      int hw = p.out_h * p.out_w;
+      int b = (int)(m / hw);
+      int r = (int)(m - (long long)b * hw);
+      ri = make_int4(b, r / p.out_w, r % p.out_w, 1);
+    }
+    rowinfo[tid] = ri;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], kProducerWarps + 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == kProducerWarps) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp < kProducerWarps) {
+    // ============================================================ producers
+    SrcView sv[DTB200_CONV_MAX_SRC];
+    int grp_end[DTB200_CONV_MAX_SRC];  // cumulative 8-channel groups per tap
+    int acc_g = 0;
+#pragma unroll
+    for (int s = 0; s < DTB200_CONV_MAX_SRC; ++s) {
+      sv[s].ptr = p.src[s];
+      sv[s].c = s < p.num_src ? p.src_c[s] : 0;
+      sv[s].resample = p.src_resample[s];
+      const bool up = sv[s].resample != DTB200_RESAMPLE_NONE;
+      sv[s].h = up ? p.in_h / 2 : p.in_h;
+      sv[s].w = up ? p.in_w / 2 : p.in_w;
+      acc_g += sv[s].c / 8;
+      grp_end[s] = acc_g;
+    }
+    const int groups_per_tap = in_c_total / 8;
+    const int total_groups = groups_per_tap * p.ksize * p.ksize;
+    const int pad = p.ksize / 2;
+    const int q = tid & 7;          // 16-byte chunk of the 128-byte row this thread fills
+    const int prow = tid >> 3;      // 0..31: rows prow, prow+32, prow+64, prow+96
+    int stage = 0, phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      // which (tap, source, channel) this thread's chunk holds in this K block
+      const int g = kb * 4 + (q >> 1);
+      const bool g_ok = g < total_groups;
+      int tap = 0, src_i = 0, c0 = 0;
+      if (g_ok) {
+        tap = g / groups_per_tap;
+        int r = g - tap * groups_per_tap;
+        src_i = r < grp_end[0] ? 0 : (r < grp_end[1] ? 1 : 2);
+        int base = src_i == 0 ? 0 : (src_i == 1 ? grp_end[0] : grp_end[1]);
+        c0 = (r - base) * 8 + (q & 1) * 4;
+      }
+      const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+      SrcView my = sv[0];
+      if (src_i == 1) my = sv[1];
+      if (src_i == 2) my = sv[2];
+
+      mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* a_big = stage_base + stage * Cfg::kStageBytes;
+      uint8_t* a_small = a_big + kATileBytes;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = prow + it * 32;
+        const int4 ri = rowinfo[row];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g_ok && ri.w) {
+          int iy = ri.y * p.stride + ky - pad, ix = ri.z * p.stride + kx - pad;
+          v = load_input4(my, ri.x, iy, ix, p.in_h, p.in_w, c0);
+        }
+        float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
+        float4 small = make_float4(v.x - big.x, v.y - big.y, v.z - big.z, v.w - big.w);
+        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
+        *reinterpret_cast<float4*>(a_big + off) = big;
+        *reinterpret_cast<float4*>(a_small + off) = small;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[stage]);
+      if (++stage == Cfg::kStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    // ============================================================ epilogue (same warps)
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row; warps 0-3 / 4-7 split the columns
+    const int4 ri = rowinfo[row];
+    constexpr int kColsPerHalf = BN / 2;
+    const int col0 = (warp >> 2) * kColsPerHalf;
+    const int n_base = n_tile * BN;
+    float* dst = p.dst + (((long long)ri.x * p.out_h + ri.y) * p.out_w + ri.z) * p.out_c + n_base;
+    const float* res = p.residual ? p.residual + (((long long)ri.x * p.out_h + ri.y) * p.out_w + ri.z) * p.out_c + n_base : nullptr;
+#pragma unroll
+    for (int cc = 0; cc < kColsPerHalf; cc += 32) {
+      float v[32];
+      tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col0 + cc), v);
+      if (ri.w) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = col0 + cc + j;
+          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (p.bias) {
+            float4 bb = ld4(p.bias + n_base + n);
+            o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
+          }
+          if (res) {
+            float4 rr = ld4(res + n);
+            o.x += rr.x, o.y += rr.y, o.z += rr.z, o.w += rr.w;
+          }
+          o.x = activate(o.x, p.act, p.act_slope);
+          o.y = activate(o.y, p.act, p.act_slope);
+          o.z = activate(o.z, p.act, p.act_slope);
+          o.w = activate(o.w, p.act, p.act_slope);
+          *reinterpret_cast<float4*>(dst + n) = o;
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ============================================================ weight loader + MMA issuer (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) +
+                             (size_t)n_tile * num_kb * (2 * Cfg::kBTileBytes);
+      int stage = 0, phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        uint8_t* a_big = stage_base + stage * Cfg::kStageBytes;
+        uint8_t* b_big = a_big + 2 * kATileBytes;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kBTileBytes);
+        bulk_g2s(b_big, wbase + (size_t)kb * (2 * Cfg::kBTileBytes), 2 * Cfg::kBTileBytes, &full[stage]);
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_big_u = smem_u32(a_big), a_small_u = a_big_u + kATileBytes;
+        const uint32_t b_big_u = a_big_u + 2 * kATileBytes, b_small_u = b_big_u + Cfg::kBTileBytes;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes along K inside the swizzled row
+          const uint64_t da_b = umma_desc_k128(a_big_u + ko), da_s = umma_desc_k128(a_small_u + ko);
+          const uint64_t db_b = umma_desc_k128(b_big_u + ko), db_s = umma_desc_k128(b_small_u + ko);
+          umma_tf32(tmem_d, da_s, db_b, idesc, (kb | ks) != 0);
+          umma_tf32(tmem_d, da_b, db_s, idesc, true);
+          umma_tf32(tmem_d, da_b, db_b, idesc, true);
+        }
+        umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(accum);  // accumulator complete
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_d);
+  }
 }
-int launch_pack_tc(const float*, float*, int, int, int, cudaStream_t) {
-  return fail(DTB200_ERR_UNSUPPORTED, "pack: math=TC3X not built yet%s");
+
+// OIHW (out_c, in_c, k, k) -> per (N tile, K block): [B_big tile | B_small tile], each [BN rows][32 fp32] in the
+// SWIZZLE_128B K-major shared-memory image; K flattened tap-major / channel-minor, zero padded to a multiple of 32.
+__global__ void pack_weight_tc_kernel(const float* __restrict__ oihw, float* __restrict__ packed, int out_c, int in_c,
+                                      int taps, int bn, int num_kb) {
+  const long long tile_floats = (long long)bn * kBK;
+  const long long total = (long long)(out_c / bn) * num_kb * tile_floats;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i / tile_floats;
+    int e = (int)(i - t * tile_floats);
+    int n_tile = (int)(t / num_kb), kb = (int)(t - (long long)n_tile * num_kb);
+    int row = e / kBK, kk = e % kBK;
+    int kflat = kb * kBK + kk;
+    float x = 0.f;
+    if (kflat < taps * in_c) {
+      int tap = kflat / in_c, c = kflat - tap * in_c;
+      x = oihw[((long long)(n_tile * bn + row) * in_c + c) * taps + tap];
+    }
+    float big = tf32_big(x);
+    float* tile = packed + t * 2 * tile_floats;
+    uint32_t off = sw128_offset(row, kk) / 4;
+    tile[off] = big;
+    tile[tile_floats + off] = x - big;
+  }
 }
-uint64_t packed_floats_tc(int out_c, int in_c, int ksize) { return (uint64_t)out_c * in_c * ksize * ksize; }
+
+int launch_conv_simt(const dtb200_conv_params& p, int in_c_total, cudaStream_t stream);
+
+uint64_t packed_floats_tc(int out_c, int in_c, int ksize) {
+  if (out_c % 64 != 0) return (uint64_t)out_c * in_c * ksize * ksize;  // heads stay on the SIMT layout
+  return (uint64_t)out_c * tc_num_kblocks(in_c, ksize) * kBK * 2;
+}
+
+int launch_pack_simt(const float* oihw, float* packed, int out_c, int in_c, int ksize, cudaStream_t s);
+
+int launch_pack_tc(const float* oihw, float* packed, int out_c, int in_c, int ksize, cudaStream_t stream) {
+  if (out_c % 64 != 0) return launch_pack_simt(oihw, packed, out_c, in_c, ksize, stream);
+  int bn = tc_bn(out_c), num_kb = tc_num_kblocks(in_c, ksize);
+  long long total = (long long)out_c * num_kb * kBK;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weight_tc_kernel<<<blocks, 256, 0, stream>>>(oihw, packed, out_c, in_c, ksize * ksize, bn, num_kb);
+  return check_launch("pack_weight_tc_kernel");
+}
+
+int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t stream) {
+  if (p.out_c % 64 != 0) return launch_conv_simt(p, in_c_total, stream);  // 1-channel heads: CUDA-core dot product
+  for (int s = 0; s < p.num_src; ++s)
+    if (p.src_c[s] % 8 != 0)
+      return fail(DTB200_ERR_UNSUPPORTED, "conv (tc3x): every source needs a multiple of 8 channels, got %s%lld", "", p.src_c[s]);
+  const long long m_total = (long long)p.batch * p.out_h * p.out_w;
+  const int num_kb = tc_num_kblocks(in_c_total, p.ksize);
+  const int bn = tc_bn(p.out_c);
+  dim3 grid((unsigned)((m_total + kBM - 1) / kBM), p.out_c / bn);
+  cudaError_t e;
+  if (bn == 128) {
+    e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes);
+    if (e != cudaSuccess) return fail(DTB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    conv_tc_kernel<128><<<grid, kThreads, TcCfg<128>::kSmemBytes, stream>>>(p, in_c_total, m_total, num_kb);
+  } else {
+    e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes);
+    if (e != cudaSuccess) return fail(DTB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    conv_tc_kernel<64><<<grid, kThreads, TcCfg<64>::kSmemBytes, stream>>>(p, in_c_total, m_total, num_kb);
+  }
+  return check_launch("conv_tc_kernel");
+}
+
 int launch_cost_volume_tc(const dtb200_cost_volume_params&, cudaStream_t) {
   return fail(DTB200_ERR_UNSUPPORTED, "cost volume: math=TC3X not built yet%s");
 }
+
 }  // namespace dtb200

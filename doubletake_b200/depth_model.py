@@ -49,10 +49,13 @@ class DepthModelCVHint(nn.Module):
 
     volume_types = {"mlp_mesh_hint_feature_volume": FeatureMeshHintVolumeManager}
 
-    def __init__(self, opts, encoder=None, matching_model=None, math="exact"):
+    def __init__(self, opts, encoder=None, matching_model=None, math="exact", volume_math=None):
+        """``math`` selects the conv-stack arithmetic ("exact": fp32 CUDA cores; "tc3x": tcgen05 3xTF32);
+        ``volume_math`` the cost-volume MLP arithmetic (defaults to "exact")."""
         super().__init__()
         self.run_opts = opts
         self.math = math
+        self.volume_math = volume_math or "exact"
         self.encoder = encoder  # image-prior encoder: image -> list of 5 maps (upstream of the boundary)
         self.matching_model = matching_model  # matching encoder: image -> (B,16,H/4,W/4) (upstream of the boundary)
         if encoder is not None and hasattr(encoder, "num_ch_enc"):
@@ -80,7 +83,7 @@ class DepthModelCVHint(nn.Module):
         self.cost_volume = self.volume_types[opts.feature_volume_type](
             matching_height=opts.image_height // (2 ** (ms + 1)), matching_width=opts.image_width // (2 ** (ms + 1)),
             num_depth_bins=opts.matching_num_depth_bins, matching_dim_size=opts.matching_feature_dims,
-            num_source_views=opts.model_num_views - 1, math=math)
+            num_source_views=opts.model_num_views - 1, math=self.volume_math)
         self._plans = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._plans.clear())
 

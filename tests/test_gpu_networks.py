@@ -26,12 +26,13 @@ def build(fx, decoder, D, prior_ch, seed, math="exact"):
     return enc.to(DEV), dec.to(DEV), encw, decw
 
 
+@pytest.mark.parametrize("math", ["exact", "tc3x"])
 @pytest.mark.parametrize("name,decoder", [("net_pp_d64", "unet_pp"), ("net_pp_d16_b2", "unet_pp"),
                                            ("net_skip_d48", "skip")])
-def test_conv_stacks_match_reference_fixture(name, decoder):
+def test_conv_stacks_match_reference_fixture(name, decoder, math):
     fx = hp.load(name)
     cfg, cv, priors, seed = hp.network_case_inputs(fx, decoder)
-    enc, dec, _, _ = build(fx, decoder, cfg.planes, cfg.prior_ch, seed)
+    enc, dec, _, _ = build(fx, decoder, cfg.planes, cfg.prior_ch, seed, math=math)
     cvf = enc(cv.to(DEV), [p.to(DEV) for p in priors[1:]])
     for i, f in enumerate(cvf):
         assert f.shape == fx[f"out.cv_feat_{i}"].shape
@@ -46,15 +47,16 @@ def test_conv_stacks_match_reference_fixture(name, decoder):
         assert hp.rel_err(out["feature_s3_b1hw"].cpu(), fx["out.feature_s3_b1hw"]) < 1e-5
 
 
+@pytest.mark.parametrize("math", ["exact", "tc3x"])
 @pytest.mark.parametrize("ih,iw,B", [(96, 160, 1), (160, 96, 2)])
-def test_odd_sizes_against_oracle(ih, iw, B):
+def test_odd_sizes_against_oracle(ih, iw, B, math):
     """Sizes whose /32 maps are odd (3x5, 5x3): partial 8x8 tiles, stride-2 convs on odd inputs."""
     fx = hp.load("net_pp_d64")
     prior_ch = (24, 48, 64, 160, 256)
     cfg = syn.WorkloadConfig("t", B, 2, ih, iw, 64, prior_ch=prior_ch, seed=51)
     priors = syn.prior_features(cfg)
     cv = torch.randn(B, 64, ih // 4, iw // 4, generator=torch.Generator().manual_seed(3))
-    enc, dec, encw, decw = build(fx, "unet_pp", 64, prior_ch, 700)
+    enc, dec, encw, decw = build(fx, "unet_pp", 64, prior_ch, 700, math=math)
     cvf = enc(cv.to(DEV), [p.to(DEV) for p in priors[1:]])
     out = dec([priors[0].to(DEV)] + cvf)
     rcvf = orc.cv_encoder(cv, priors[1:], encw)
@@ -65,7 +67,8 @@ def test_odd_sizes_against_oracle(ih, iw, B):
         assert float((out[k].cpu() - ref[k]).abs().max()) < 1e-4
 
 
-def test_single_conv_features_against_torch():
+@pytest.mark.parametrize("math", ["exact", "tc3x"])
+def test_single_conv_features_against_torch(math):
     """Each fused feature of dtb200_conv2d in isolation: concat of 3 sources, bilinear / nearest x2 on load, stride 2,
     1x1, residual, LeakyReLU / ELU -- against F.conv2d on CPU."""
     import torch.nn as nn
@@ -77,7 +80,7 @@ def test_single_conv_features_against_torch():
     c = torch.randn(B, 8, H // 2, W // 2, generator=g)
     res = torch.randn(B, 64, H, W, generator=g)
     conv = nn.Conv2d(48, 64, 3, padding=1)
-    plan = dt.ConvPlan(torch.device(DEV), "exact")
+    plan = dt.ConvPlan(torch.device(DEV), math)
     fa, fb, fc = plan.input("a", *a.shape), plan.input("b", *b.shape), plan.input("c", *c.shape)
     fr = plan.input("r", *res.shape)
     o1 = plan.conv([(fa, L.RESAMPLE_NONE), (fb, L.RESAMPLE_BILINEAR_UP2), (fc, L.RESAMPLE_NEAREST_UP2)], conv,
