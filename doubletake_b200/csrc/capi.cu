@@ -11,6 +11,8 @@ int launch_pack_simt(const float* oihw, float* packed, int out_c, int in_c, int 
 int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t stream);                    // conv_tc.cu
 int launch_pack_tc(const float* oihw, float* packed, int out_c, int in_c, int ksize, cudaStream_t s);    // conv_tc.cu
 uint64_t packed_floats_tc(int out_c, int in_c, int ksize);                                               // conv_tc.cu
+uint64_t conv_tc_workspace_bytes(const dtb200_conv_params& p, int in_c_total);                           // conv_tc.cu
+int launch_resample_copy(const dtb200_conv_params& p, cudaStream_t stream);                              // conv_tc.cu
 
 // (N,C,H,W) <-> (N,H,W,C): 32x32 smem tile transpose of the (C, H*W) matrix of each sample.
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
@@ -137,8 +139,16 @@ extern "C" int dtb200_pack_conv_weight(int32_t math, const float* oihw, float* p
   return fail(DTB200_ERR_INVALID, "pack_conv_weight: unknown math mode%s");
 }
 
+extern "C" uint64_t dtb200_conv_workspace_bytes(const dtb200_conv_params* p) {
+  if (!p || p->math != DTB200_MATH_TC3X || p->ksize == 0) return 0;
+  int total = 0;
+  for (int s = 0; s < p->num_src && s < DTB200_CONV_MAX_SRC; ++s) total += p->src_c[s];
+  return conv_tc_workspace_bytes(*p, total);
+}
+
 extern "C" int dtb200_conv2d(const dtb200_conv_params* p, dtb200_stream_t stream) {
   if (!p) return fail(DTB200_ERR_INVALID, "conv: null params%s");
+  if (p->ksize == 0) return launch_resample_copy(*p, (cudaStream_t)stream);
   int total = 0;
   int rc = conv_total_in_c(*p, total);
   if (rc != DTB200_OK) return rc;

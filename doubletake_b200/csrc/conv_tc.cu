@@ -44,7 +44,7 @@ __host__ __device__ inline int tc_bn(int out_c) { return (out_c % 128 == 0) ? 12
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, TcCfg<BN>::kMinBlocks) conv_tc_kernel(const dtb200_conv_params p, int in_c_total, long long m_total,
-                                                           int num_kb) {
+                                                           int num_kb_total, int kb_per_split, float* __restrict__ partial) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -59,6 +59,9 @@ __global__ void __launch_bounds__(kThreads, TcCfg<BN>::kMinBlocks) conv_tc_kerne
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long m0 = (long long)blockIdx.x * kBM;
   const int n_tile = blockIdx.y;
+  // split-K: this CTA owns K blocks [kb_begin, kb_begin + num_kb)
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int num_kb = min(kb_per_split, num_kb_total - kb_begin);
 
   if (tid < kBM) {
     long long m = m0 + tid;
@@ -106,9 +109,29 @@ __global__ void __launch_bounds__(kThreads, TcCfg<BN>::kMinBlocks) conv_tc_kerne
     const int pad = p.ksize / 2;
     const int q = tid & 7;          // 16-byte chunk of the 128-byte row this thread fills
     const int prow = tid >> 3;      // 0..31: rows prow, prow+32, prow+64, prow+96
-    int stage = 0, phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      // which (tap, source, channel) this thread's chunk holds in this K block
+    // per-row state kept in registers for the whole tile: centre-tap pixel index in the conv input, 9-bit tap validity
+    // mask (zero padding), shared-memory byte offset of this thread's chunk
+    int pix_center[4];
+    uint32_t tap_mask[4], soff[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = prow + it * 32;
+      const int4 ri = rowinfo[row];
+      const int cy = ri.y * p.stride, cx = ri.z * p.stride;
+      pix_center[it] = (ri.x * p.in_h + cy) * p.in_w + cx;
+      uint32_t mask = 0;
+      if (ri.w) {
+        for (int t = 0; t < p.ksize * p.ksize; ++t) {
+          int iy = cy + t / p.ksize - pad, ix = cx + t % p.ksize - pad;
+          if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) mask |= 1u << t;
+        }
+      }
+      tap_mask[it] = mask;
+      soff[it] = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
+    }
+
+    // gather this thread's 4 chunks of K block kb into registers (loads only; nothing is waited on here)
+    auto gather = [&](int kb, float4 (&v)[4]) {
       const int g = kb * 4 + (q >> 1);
       const bool g_ok = g < total_groups;
       int tap = 0, src_i = 0, c0 = 0;
@@ -123,24 +146,45 @@ __global__ void __launch_bounds__(kThreads, TcCfg<BN>::kMinBlocks) conv_tc_kerne
       SrcView my = sv[0];
       if (src_i == 1) my = sv[1];
       if (src_i == 2) my = sv[2];
+      if (my.resample == DTB200_RESAMPLE_NONE) {
+        // fast path: one add per row on top of the cached centre index
+        const int dpix = (ky - pad) * p.in_w + (kx - pad);
+        const float* base = my.ptr + c0;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const bool ok = g_ok && ((tap_mask[it] >> tap) & 1u);
+          v[it] = ok ? ld4(base + (long long)(pix_center[it] + dpix) * my.c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        // generic path: x2 up-sampling on load (the TC plans normally materialise up-sampled maps instead)
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int4 ri = rowinfo[prow + it * 32];
+          v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g_ok && ri.w) {
+            int iy = ri.y * p.stride + ky - pad, ix = ri.z * p.stride + kx - pad;
+            v[it] = load_input4(my, ri.x, iy, ix, p.in_h, p.in_w, c0);
+          }
+        }
+      }
+    };
 
+    int stage = 0, phase = 0;
+    float4 cur[4], nxt[4];
+    gather(kb_begin, cur);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      // software pipeline: the next K block's global loads are in flight while this one is split and stored
+      if (kb + 1 < num_kb) gather(kb_begin + kb + 1, nxt);
       mbar_wait(&empty[stage], phase ^ 1);
       uint8_t* a_big = stage_base + stage * Cfg::kStageBytes;
       uint8_t* a_small = a_big + kATileBytes;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const int row = prow + it * 32;
-        const int4 ri = rowinfo[row];
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g_ok && ri.w) {
-          int iy = ri.y * p.stride + ky - pad, ix = ri.z * p.stride + kx - pad;
-          v = load_input4(my, ri.x, iy, ix, p.in_h, p.in_w, c0);
-        }
+        const float4 v = cur[it];
         float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
         float4 small = make_float4(v.x - big.x, v.y - big.y, v.z - big.z, v.w - big.w);
-        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
-        *reinterpret_cast<float4*>(a_big + off) = big;
-        *reinterpret_cast<float4*>(a_small + off) = small;
+        *reinterpret_cast<float4*>(a_big + soff[it]) = big;
+        *reinterpret_cast<float4*>(a_small + soff[it]) = small;
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -149,6 +193,8 @@ __global__ void __launch_bounds__(kThreads, TcCfg<BN>::kMinBlocks) conv_tc_kerne
         stage = 0;
         phase ^= 1;
       }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
     }
     // ============================================================ epilogue (same warps)
     mbar_wait(accum, 0);
@@ -164,7 +210,14 @@ __global__ void __launch_bounds__(kThreads, TcCfg<BN>::kMinBlocks) conv_tc_kerne
     for (int cc = 0; cc < kColsPerHalf; cc += 32) {
       float v[32];
       tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col0 + cc), v);
-      if (ri.w) {
+      if (partial) {
+        // split-K: raw fp32 partial sums -> workspace[split][m][out_c]; bias/residual/activation happen in the reducer
+        if (ri.w) {
+          float* w = partial + ((long long)blockIdx.z * m_total + (m0 + row)) * p.out_c + n_base + col0 + cc;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(w + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      } else if (ri.w) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const int n = col0 + cc + j;
@@ -191,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, TcCfg<BN>::kMinBlocks) conv_tc_kerne
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) +
-                             (size_t)n_tile * num_kb * (2 * Cfg::kBTileBytes);
+                             ((size_t)n_tile * num_kb_total + kb_begin) * (2 * Cfg::kBTileBytes);
       int stage = 0, phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         uint8_t* a_big = stage_base + stage * Cfg::kStageBytes;
@@ -273,26 +326,123 @@ int launch_pack_tc(const float* oihw, float* packed, int out_c, int in_c, int ks
   return check_launch("pack_weight_tc_kernel");
 }
 
+// split-K plan: enough CTAs to fill the machine when the (M, N) grid alone cannot, >= 4 K blocks per split
+static int tc_splits(long long m_total, int out_c, int num_kb) {
+  const int bn = tc_bn(out_c);
+  const long long ctas = ((m_total + kBM - 1) / kBM) * (out_c / bn);
+  if (ctas >= 148) return 1;
+  int splits = (int)((2 * 148 + ctas - 1) / ctas);
+  int max_splits = num_kb / 4;
+  if (splits > max_splits) splits = max_splits;
+  if (splits > 32) splits = 32;
+  return splits < 1 ? 1 : splits;
+}
+
+uint64_t conv_tc_workspace_bytes(const dtb200_conv_params& p, int in_c_total) {
+  if (p.ksize == 0 || p.out_c % 64 != 0) return 0;
+  const long long m_total = (long long)p.batch * p.out_h * p.out_w;
+  const int splits = tc_splits(m_total, p.out_c, tc_num_kblocks(in_c_total, p.ksize));
+  return splits > 1 ? (uint64_t)splits * m_total * p.out_c * sizeof(float) : 0;
+}
+
+// Deterministic split-K reduction (splits summed in order) fused with bias / residual / activation.
+__global__ void splitk_epilogue_kernel(const float* __restrict__ partial, int splits, long long mn, int out_c,
+                                       const float* __restrict__ bias, const float* __restrict__ residual, int act,
+                                       float slope, float* __restrict__ dst) {
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < mn; i += (long long)gridDim.x * blockDim.x * 4) {
+    float4 a = ld4(partial + i);
+    for (int s = 1; s < splits; ++s) {
+      float4 b = ld4(partial + (long long)s * mn + i);
+      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    }
+    const int n = (int)(i % out_c);
+    if (bias) {
+      float4 b = ld4(bias + n);
+      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    }
+    if (residual) {
+      float4 r = ld4(residual + i);
+      a.x += r.x, a.y += r.y, a.z += r.z, a.w += r.w;
+    }
+    a.x = activate(a.x, act, slope), a.y = activate(a.y, act, slope);
+    a.z = activate(a.z, act, slope), a.w = activate(a.w, act, slope);
+    *reinterpret_cast<float4*>(dst + i) = a;
+  }
+}
+
+// ksize == 0 descriptor: dst = resample(src[0]) (x2 bilinear / nearest), written once so the tensor-core convs that
+// consume it (3x3 conv1 and the 1x1 skip projection) read plain channels-last data instead of interpolating 10 times.
+__global__ void resample_copy_kernel(const dtb200_conv_params p) {
+  SrcView sv;
+  sv.ptr = p.src[0];
+  sv.c = p.src_c[0];
+  sv.resample = p.src_resample[0];
+  sv.h = p.in_h / 2;
+  sv.w = p.in_w / 2;
+  const int c4 = sv.c / 4;
+  const long long total = (long long)p.batch * p.in_h * p.in_w * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % c4) * 4;
+    long long pix = i / c4;
+    int x = (int)(pix % p.in_w);
+    long long r = pix / p.in_w;
+    int y = (int)(r % p.in_h), b = (int)(r / p.in_h);
+    float4 v = load_input4(sv, b, y, x, p.in_h, p.in_w, c);
+    *reinterpret_cast<float4*>(p.dst + pix * sv.c + c) = v;
+  }
+}
+
+int launch_resample_copy(const dtb200_conv_params& p, cudaStream_t stream) {
+  if (p.num_src != 1 || p.src_resample[0] == DTB200_RESAMPLE_NONE || p.src_c[0] % 4 != 0 || p.out_c != p.src_c[0] ||
+      p.out_h != p.in_h || p.out_w != p.in_w || (p.in_h & 1) || (p.in_w & 1) || !p.src[0] || !p.dst)
+    return fail(DTB200_ERR_INVALID, "resample copy (ksize=0): needs one x2-resampled source and a matching dst%s");
+  long long total = (long long)p.batch * p.in_h * p.in_w * (p.src_c[0] / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  resample_copy_kernel<<<blocks, 256, 0, stream>>>(p);
+  return check_launch("resample_copy_kernel");
+}
+
 int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t stream) {
   if (p.out_c % 64 != 0) return launch_conv_simt(p, in_c_total, stream);  // 1-channel heads: CUDA-core dot product
   for (int s = 0; s < p.num_src; ++s)
     if (p.src_c[s] % 8 != 0)
       return fail(DTB200_ERR_UNSUPPORTED, "conv (tc3x): every source needs a multiple of 8 channels, got %s%lld", "", p.src_c[s]);
   const long long m_total = (long long)p.batch * p.out_h * p.out_w;
+  if (m_total * (long long)in_c_total >= (1LL << 31) || (long long)p.batch * p.in_h * p.in_w >= (1LL << 31) / 1024)
+    return fail(DTB200_ERR_UNSUPPORTED, "conv (tc3x): tensor too large for 32-bit pixel indexing%s");
   const int num_kb = tc_num_kblocks(in_c_total, p.ksize);
   const int bn = tc_bn(p.out_c);
-  dim3 grid((unsigned)((m_total + kBM - 1) / kBM), p.out_c / bn);
+  const int splits = tc_splits(m_total, p.out_c, num_kb);
+  float* partial = nullptr;
+  if (splits > 1) {
+    uint64_t need = (uint64_t)splits * m_total * p.out_c * sizeof(float);
+    if (!p.workspace || p.workspace_bytes < need)
+      return fail(DTB200_ERR_INVALID, "conv (tc3x): split-K needs %s%lld workspace bytes (dtb200_conv_workspace_bytes)", "",
+                  (long long)need);
+    partial = reinterpret_cast<float*>(p.workspace);
+  }
+  const int kb_per_split = (num_kb + splits - 1) / splits;
+  const int zsplits = (num_kb + kb_per_split - 1) / kb_per_split;
+  dim3 grid((unsigned)((m_total + kBM - 1) / kBM), p.out_c / bn, zsplits);
   cudaError_t e;
   if (bn == 128) {
     e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes);
     if (e != cudaSuccess) return fail(DTB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    conv_tc_kernel<128><<<grid, kThreads, TcCfg<128>::kSmemBytes, stream>>>(p, in_c_total, m_total, num_kb);
+    conv_tc_kernel<128><<<grid, kThreads, TcCfg<128>::kSmemBytes, stream>>>(p, in_c_total, m_total, num_kb, kb_per_split, partial);
   } else {
     e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes);
     if (e != cudaSuccess) return fail(DTB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    conv_tc_kernel<64><<<grid, kThreads, TcCfg<64>::kSmemBytes, stream>>>(p, in_c_total, m_total, num_kb);
+    conv_tc_kernel<64><<<grid, kThreads, TcCfg<64>::kSmemBytes, stream>>>(p, in_c_total, m_total, num_kb, kb_per_split, partial);
   }
-  return check_launch("conv_tc_kernel");
+  int rc = check_launch("conv_tc_kernel");
+  if (rc != DTB200_OK || !partial) return rc;
+  const long long mn = m_total * p.out_c;
+  int blocks = (int)((mn / 4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  splitk_epilogue_kernel<<<blocks, 256, 0, stream>>>(partial, zsplits, mn, p.out_c, p.bias, p.residual, p.act, p.act_slope,
+                                                     p.dst);
+  return check_launch("splitk_epilogue_kernel");
 }
 
 int launch_cost_volume_tc(const dtb200_cost_volume_params&, cudaStream_t) {

@@ -44,7 +44,9 @@ class ConvPlan:
         self.keep = []  # tensors referenced by raw pointers
         self.inputs = {}  # name -> Feature filled from an NCHW tensor before run()
         self._packed = {}
+        self._upsampled = {}
         self._array = None
+        self.workspace = None
 
     def new(self, b, h, w, c):
         t = torch.empty((b, h, w, c), dtype=torch.float32, device=self.device)
@@ -68,8 +70,27 @@ class ConvPlan:
             self.keep.append(packed)
         return self._packed[key]
 
+    def upsampled(self, f: Feature, mode):
+        """Materialise the x2 up-sampled map once (resample descriptor, ksize = 0) and share it between consumers."""
+        key = (id(f), mode)
+        if key not in self._upsampled:
+            out = self.new(f.b, 2 * f.h, 2 * f.w, f.c)
+            op = L.ConvParams()
+            op.math, op.batch = self.math, f.b
+            op.in_h = op.out_h = 2 * f.h
+            op.in_w = op.out_w = 2 * f.w
+            op.out_c, op.ksize, op.stride, op.num_src = f.c, 0, 1, 1
+            op.src[0], op.src_c[0], op.src_resample[0] = L.ptr(f.t), f.c, mode
+            op.dst = L.ptr(out.t)
+            self.ops.append(op)
+            self._upsampled[key] = out
+        return self._upsampled[key]
+
     def conv(self, srcs, conv: nn.Conv2d, act=L.ACT_NONE, slope=0.0, residual=None):
         """srcs: list of (Feature, resample).  Returns the output Feature."""
+        if self.math == L.MATH_TC3X and conv.out_channels % 64 == 0:
+            # tensor-core path: interpolate once, not once per tap per consumer
+            srcs = [(self.upsampled(f, r), L.RESAMPLE_NONE) if r != L.RESAMPLE_NONE else (f, r) for f, r in srcs]
         k = conv.kernel_size[0]
         stride = conv.stride[0]
         f0, r0 = srcs[0]
@@ -108,12 +129,19 @@ class ConvPlan:
         return out
 
     def finalize(self):
+        need = max([int(L.lib().dtb200_conv_workspace_bytes(C.byref(op))) for op in self.ops] + [0])
+        if need:
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+            for op in self.ops:
+                op.workspace, op.workspace_bytes = L.ptr(self.workspace), need
         self._array = (L.ConvParams * len(self.ops))(*self.ops)
         return self
 
     def flops(self):
         total = 0
         for op in self.ops:
+            if op.ksize == 0:
+                continue
             cin = sum(op.src_c[i] for i in range(op.num_src))
             total += 2 * op.batch * op.out_h * op.out_w * op.out_c * cin * op.ksize * op.ksize
         return total

@@ -137,7 +137,16 @@ typedef struct {
   int32_t act;
   float act_slope;
   float* dst;            /* NHWC (B,out_h,out_w,out_c) */
+  /* scratch for split-K partial sums (math = TC3X on small maps); size from dtb200_conv_workspace_bytes, may be NULL
+   * when that returns 0.  Launches of one sequence run in stream order, so one buffer can serve all of them. */
+  void* workspace;
+  uint64_t workspace_bytes;
 } dtb200_conv_params;
+
+/* ksize == 0 is a pure resample descriptor: dst = resample(src[0]) with src_resample[0] in {BILINEAR_UP2, NEAREST_UP2},
+ * out_c == src_c[0], out size == in size (the up-sampled size); weight/bias/residual ignored.  The tensor-core plans
+ * materialise an up-sampled map once with it instead of interpolating inside every consumer. */
+uint64_t dtb200_conv_workspace_bytes(const dtb200_conv_params* p);
 
 /* floats needed for the packed copy of an (out_c, in_c, k, k) OIHW weight */
 uint64_t dtb200_packed_conv_weight_floats(int32_t math, int32_t out_c, int32_t in_c, int32_t ksize);

@@ -11,6 +11,10 @@ from doubletake_b200 import synthetic as syn
 from oracle import oracle_torch as orc
 
 pytestmark = pytest.mark.gpu
+# feature-map tolerance (relative to the map's max): exact = fp32 FMA in a fixed order; tc3x = 3xTF32 on tcgen05, whose
+# fp32 TMEM accumulation truncates instead of rounding (measured ~2e-5 over K up to 5760).  The contract that matters,
+# depth within 1e-4 relative, is asserted on the network outputs below and in test_gpu_model.py for both modes.
+FEAT_TOL = {"exact": 1e-5, "tc3x": 5e-5}
 torch.set_grad_enabled(False)
 DEV = "cuda"
 
@@ -36,7 +40,7 @@ def test_conv_stacks_match_reference_fixture(name, decoder, math):
     cvf = enc(cv.to(DEV), [p.to(DEV) for p in priors[1:]])
     for i, f in enumerate(cvf):
         assert f.shape == fx[f"out.cv_feat_{i}"].shape
-        assert hp.rel_err(f.cpu(), fx[f"out.cv_feat_{i}"]) < 1e-5
+        assert hp.rel_err(f.cpu(), fx[f"out.cv_feat_{i}"]) < FEAT_TOL[math]
     out = dec([priors[0].to(DEV)] + cvf)
     for i in range(4):
         k = f"log_depth_pred_s{i}_b1hw"
@@ -44,7 +48,7 @@ def test_conv_stacks_match_reference_fixture(name, decoder, math):
         assert out[k].shape == ref.shape
         assert float((out[k].cpu() - ref).abs().max()) < 1e-4, k
     if decoder == "skip":
-        assert hp.rel_err(out["feature_s3_b1hw"].cpu(), fx["out.feature_s3_b1hw"]) < 1e-5
+        assert hp.rel_err(out["feature_s3_b1hw"].cpu(), fx["out.feature_s3_b1hw"]) < FEAT_TOL[math]
 
 
 @pytest.mark.parametrize("math", ["exact", "tc3x"])
@@ -62,7 +66,7 @@ def test_odd_sizes_against_oracle(ih, iw, B, math):
     rcvf = orc.cv_encoder(cv, priors[1:], encw)
     ref = orc.depth_decoder_pp(priors[:1] + rcvf, decw)
     for i in range(4):
-        assert hp.rel_err(cvf[i].cpu(), rcvf[i]) < 1e-5
+        assert hp.rel_err(cvf[i].cpu(), rcvf[i]) < FEAT_TOL[math]
         k = f"log_depth_pred_s{i}_b1hw"
         assert float((out[k].cpu() - ref[k]).abs().max()) < 1e-4
 
@@ -103,4 +107,4 @@ def test_single_conv_features_against_torch(math):
     for o, r in ((o1, r1), (o2, r2), (o3, r3), (o4, r4)):
         got = o.t.cpu().permute(0, 3, 1, 2)
         assert got.shape == r.shape
-        assert hp.rel_err(got, r) < 1e-5
+        assert hp.rel_err(got, r) < FEAT_TOL[math]
