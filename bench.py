@@ -177,7 +177,7 @@ def run_b200(args):
     cfg = syn.CONFIGS[WORKLOAD]
     opts = dt.HotPathOptions(matching_num_depth_bins=cfg.planes, model_num_views=cfg.num_src + 1,
                              image_height=cfg.image_h, image_width=cfg.image_w)
-    model = dt.DepthModelCVHint(opts, math=args.math)
+    model = dt.DepthModelCVHint(opts, math=args.math, volume_math=args.volume_math or args.math)
     model.load_state_dict(model_weights(model), strict=False)
     model = model.to(dev)
 
@@ -457,6 +457,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--math", default="exact", choices=["exact", "tc3x"])
+    ap.add_argument("--volume-math", default=None, choices=["exact", "tc3x"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--ref-budget", type=float, default=150.0)

@@ -34,7 +34,7 @@ class CostVolumeParams(C.Structure):
         ("w1", fp), ("b1", fp), ("w2", fp), ("b2", fp), ("w3", fp), ("b3", fp),
         ("hw1", fp), ("hb1", fp), ("hw2", fp), ("hb2", fp), ("hw3", fp), ("hb3", fp),
         ("volume", fp), ("lowest_cost", fp), ("best_index", fp), ("mask_views", fp), ("mask_any", fp),
-        ("workspace", fp), ("workspace_bytes", C.c_uint64),
+        ("workspace", fp), ("workspace_bytes", C.c_uint64), ("workspace_prepared", C.c_int32),
     ]
 
 
@@ -60,6 +60,7 @@ SYMBOLS = {
     "dtb200_nchw_to_nhwc": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),
     "dtb200_nhwc_to_nchw": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),
     "dtb200_cost_volume_workspace_bytes": (C.c_uint64, [C.POINTER(CostVolumeParams)]),
+    "dtb200_cost_volume_prepare": (C.c_int, [C.POINTER(CostVolumeParams), fp]),
     "dtb200_cost_volume": (C.c_int, [C.POINTER(CostVolumeParams), fp]),
     "dtb200_packed_conv_weight_floats": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dtb200_pack_conv_weight": (C.c_int, [C.c_int32, fp, fp, C.c_int32, C.c_int32, C.c_int32, fp]),

@@ -186,9 +186,18 @@ class CostVolumeManager(nn.Module):
         p.mask_views, p.mask_any = L.ptr(mask_views), L.ptr(mask_any)
         ws = int(L.lib().dtb200_cost_volume_workspace_bytes(C.byref(p)))
         if ws:
-            work = torch.empty(ws, dtype=torch.uint8, device=dev)
-            keep.append(work)
-            p.workspace, p.workspace_bytes = L.ptr(work), ws
+            # tensor-core weight tiles: re-tiled once per weight version, then reused
+            w = self._mlp_weights()
+            key = (str(dev), ws) + tuple((t.data_ptr(), t._version) for t in (w["w1"], w["w2"]))
+            cache = self.__dict__.setdefault("_tc_workspace", {})
+            if key not in cache:
+                cache.clear()
+                work = torch.empty(ws, dtype=torch.uint8, device=dev)
+                p.workspace, p.workspace_bytes = L.ptr(work), ws
+                L.check(L.lib().dtb200_cost_volume_prepare(C.byref(p), L.stream()))
+                cache[key] = work
+            work = cache[key]
+            p.workspace, p.workspace_bytes, p.workspace_prepared = L.ptr(work), ws, 1
         L.check(L.lib().dtb200_cost_volume(C.byref(p), L.stream()))
 
         mask = None

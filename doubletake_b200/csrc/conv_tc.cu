@@ -445,8 +445,4 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
   return check_launch("splitk_epilogue_kernel");
 }
 
-int launch_cost_volume_tc(const dtb200_cost_volume_params&, cudaStream_t) {
-  return fail(DTB200_ERR_UNSUPPORTED, "cost volume: math=TC3X not built yet%s");
-}
-
 }  // namespace dtb200

@@ -95,12 +95,16 @@ typedef struct {
   int32_t* best_index;  /* (B,H,W) arg-max plane index; may be NULL */
   uint8_t* mask_views;  /* (B,K,H,W) last-plane depth-valid & in-bounds per view; may be NULL */
   uint8_t* mask_any;    /* (B,H,W) any_k(depth-valid) & any_k(in-bounds) on the last plane; may be NULL */
-  /* scratch for math = TC3X (see dtb200_cost_volume_workspace_bytes); may be NULL otherwise */
+  /* math = TC3X: device scratch holding the MLP weights re-tiled for the tensor cores (size from
+   * dtb200_cost_volume_workspace_bytes).  dtb200_cost_volume_prepare fills it; set workspace_prepared = 1 to reuse it on
+   * later calls with the same weights (otherwise every call re-tiles first).  NULL / 0 for the other modes. */
   void* workspace;
   uint64_t workspace_bytes;
+  int32_t workspace_prepared;
 } dtb200_cost_volume_params;
 
 uint64_t dtb200_cost_volume_workspace_bytes(const dtb200_cost_volume_params* p);
+int dtb200_cost_volume_prepare(const dtb200_cost_volume_params* p, dtb200_stream_t stream);
 int dtb200_cost_volume(const dtb200_cost_volume_params* p, dtb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -72,6 +72,7 @@ def argmax_mismatch_report(volume, ref_index, tol=1e-5):
     v_ref = torch.gather(volume, 1, ref_index.unsqueeze(1)).squeeze(1)
     gap = (v_ours - v_ref).abs()[bad]
     scale = float(volume.abs().max())
+    argmax_mismatch_report.last = dict(n_bad=n_bad, max_rel_gap=float(gap.max()) / scale, scale=scale)
     return n_bad, int((gap > tol * scale).sum())
 
 
