@@ -24,74 +24,82 @@ namespace dtb200 {
 
 using namespace tc;
 
-constexpr int kBM = 128;                 // pixels per CTA tile (UMMA M)
+constexpr int kBM = 128;                 // pixels per tile (UMMA M)
 constexpr int kBK = 32;                  // fp32 per K block = one 128-byte swizzled row
 constexpr int kProducerWarps = 8;
-constexpr int kThreads = (kProducerWarps + 1) * 32;
-constexpr int kATileBytes = kBM * 128;   // 16 KB
+constexpr int kEpilogueWarps = 4;
+constexpr int kMmaWarp = kProducerWarps + kEpilogueWarps;      // 12
+constexpr int kLoaderWarp = kMmaWarp + 1;                      // 13
+constexpr int kThreads = (kLoaderWarp + 1) * 32;               // 448
+constexpr int kATileBytes = kBM * 128;   // 16 KB (one of big / small)
+constexpr int kAStageBytes = 2 * kATileBytes;
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kBTileBytes = BN * 128;
-  static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;  // A_big, A_small, B_big, B_small
-  static constexpr int kStages = BN <= 64 ? 2 : 3;
-  static constexpr int kMinBlocks = BN <= 64 ? 2 : 1;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 2048 /*row info*/ + 256 /*barriers*/;
+  static constexpr int kBStageBytes = 2 * BN * 128;  // B_big | B_small
+  static constexpr int kAStages = BN <= 64 ? 4 : 3;
+  static constexpr int kBStages = BN <= 64 ? 4 : 3;
+  static constexpr int kTmemCols = 2 * BN;           // two accumulators
+  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 __host__ __device__ inline int tc_num_kblocks(int in_c, int ksize) { return (in_c * ksize * ksize + kBK - 1) / kBK; }
 __host__ __device__ inline int tc_bn(int out_c) { return (out_c % 128 == 0) ? 128 : 64; }
 
+struct TcWork {  // persistent tile scheduler: item -> (m tile, n tile, K split)
+  int m_tiles, n_tiles, splits, kb_per_split, num_kb_total;
+  long long total;
+};
+
+// Persistent warp-specialised implicit-GEMM conv.  One CTA per SM loops over work items (static stride).
+//   warps 0-7   A producers: im2col gather -> 3xTF32 split -> SWIZZLE_128B tiles (4-deep ring)
+//   warps 8-11  epilogue: TMEM -> bias/residual/activation -> NHWC store (or split-K partials); double-buffered accumulator
+//   warp 12     MMA issuer (one lane): 12 tcgen05.mma per K block, tcgen05.commit frees the A and B stages
+//   warp 13     weight-tile loader (one lane): cp.async.bulk of the pre-swizzled [B_big|B_small] tile, running ahead
 template <int BN>
-__global__ void __launch_bounds__(kThreads, TcCfg<BN>::kMinBlocks) conv_tc_kernel(const dtb200_conv_params p, int in_c_total, long long m_total,
-                                                           int num_kb_total, int kb_per_split, float* __restrict__ partial) {
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_params p, int in_c_total, long long m_total,
+                                                              TcWork wk, float* __restrict__ partial) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* stage_base = smem;
-  int4* rowinfo = reinterpret_cast<int4*>(smem + Cfg::kStages * Cfg::kStageBytes);  // [128] {b, oy, ox, valid}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rowinfo) + 2048);
-  uint64_t* full = bars;                       // [kStages]
-  uint64_t* empty = bars + Cfg::kStages;       // [kStages]
-  uint64_t* accum = bars + 2 * Cfg::kStages;   // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 1);
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + Cfg::kAStages * kAStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + Cfg::kBStages * Cfg::kBStageBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + Cfg::kAStages;
+  uint64_t* b_full = a_empty + Cfg::kAStages;
+  uint64_t* b_empty = b_full + Cfg::kBStages;
+  uint64_t* acc_full = b_empty + Cfg::kBStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long m0 = (long long)blockIdx.x * kBM;
-  const int n_tile = blockIdx.y;
-  // split-K: this CTA owns K blocks [kb_begin, kb_begin + num_kb)
-  const int kb_begin = blockIdx.z * kb_per_split;
-  const int num_kb = min(kb_per_split, num_kb_total - kb_begin);
-
-  if (tid < kBM) {
-    long long m = m0 + tid;
-    int4 ri = make_int4(0, 0, 0, 0);
-    if (m < m_total) {
-      int hw = p.out_h * p.out_w;
-      int b = (int)(m / hw);
-      int r = (int)(m - (long long)b * hw);
-      ri = make_int4(b, r / p.out_w, r % p.out_w, 1);
-    }
-    rowinfo[tid] = ri;
-  }
   if (tid == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full[s], kProducerWarps + 1);
-      mbar_init(&empty[s], 1);
-    }
-    mbar_init(accum, 1);
+    for (int s = 0; s < Cfg::kAStages; ++s) mbar_init(&a_full[s], kProducerWarps), mbar_init(&a_empty[s], 1);
+    for (int s = 0; s < Cfg::kBStages; ++s) mbar_init(&b_full[s], 1), mbar_init(&b_empty[s], 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&acc_full[s], 1), mbar_init(&acc_empty[s], kEpilogueWarps);
     fence_mbar_init();
   }
-  if (warp == kProducerWarps) tmem_alloc<BN>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
+  const int hw = p.out_h * p.out_w;
+
+  auto decode = [&](long long item, int& m_tile, int& n_tile, int& kb_begin, int& num_kb, int& split) {
+    split = (int)(item % wk.splits);
+    long long r = item / wk.splits;
+    n_tile = (int)(r % wk.n_tiles);
+    m_tile = (int)(r / wk.n_tiles);
+    kb_begin = split * wk.kb_per_split;
+    num_kb = min(wk.kb_per_split, wk.num_kb_total - kb_begin);
+  };
 
   if (warp < kProducerWarps) {
-    // ============================================================ producers
+    // ============================================================ A producers
     SrcView sv[DTB200_CONV_MAX_SRC];
-    int grp_end[DTB200_CONV_MAX_SRC];  // cumulative 8-channel groups per tap
+    int grp_end[DTB200_CONV_MAX_SRC];
     int acc_g = 0;
 #pragma unroll
     for (int s = 0; s < DTB200_CONV_MAX_SRC; ++s) {
@@ -105,180 +113,223 @@ __global__ void __launch_bounds__(kThreads, TcCfg<BN>::kMinBlocks) conv_tc_kerne
       grp_end[s] = acc_g;
     }
     const int groups_per_tap = in_c_total / 8;
-    const int total_groups = groups_per_tap * p.ksize * p.ksize;
+    const int taps = p.ksize * p.ksize;
     const int pad = p.ksize / 2;
     const int q = tid & 7;          // 16-byte chunk of the 128-byte row this thread fills
-    const int prow = tid >> 3;      // 0..31: rows prow, prow+32, prow+64, prow+96
-    // per-row state kept in registers for the whole tile: centre-tap pixel index in the conv input, 9-bit tap validity
-    // mask (zero padding), shared-memory byte offset of this thread's chunk
-    int pix_center[4];
-    uint32_t tap_mask[4], soff[4];
+    const int prow = tid >> 3;      // rows prow, prow+32, prow+64, prow+96
+    uint32_t soff[4];
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int row = prow + it * 32;
-      const int4 ri = rowinfo[row];
-      const int cy = ri.y * p.stride, cx = ri.z * p.stride;
-      pix_center[it] = (ri.x * p.in_h + cy) * p.in_w + cx;
-      uint32_t mask = 0;
-      if (ri.w) {
-        for (int t = 0; t < p.ksize * p.ksize; ++t) {
-          int iy = cy + t / p.ksize - pad, ix = cx + t % p.ksize - pad;
-          if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) mask |= 1u << t;
-        }
-      }
-      tap_mask[it] = mask;
       soff[it] = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
     }
-
-    // gather this thread's 4 chunks of K block kb into registers (loads only; nothing is waited on here)
-    auto gather = [&](int kb, float4 (&v)[4]) {
-      const int g = kb * 4 + (q >> 1);
-      const bool g_ok = g < total_groups;
-      int tap = 0, src_i = 0, c0 = 0;
-      if (g_ok) {
-        tap = g / groups_per_tap;
-        int r = g - tap * groups_per_tap;
-        src_i = r < grp_end[0] ? 0 : (r < grp_end[1] ? 1 : 2);
-        int base = src_i == 0 ? 0 : (src_i == 1 ? grp_end[0] : grp_end[1]);
-        c0 = (r - base) * 8 + (q & 1) * 4;
-      }
-      const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-      SrcView my = sv[0];
-      if (src_i == 1) my = sv[1];
-      if (src_i == 2) my = sv[2];
-      if (my.resample == DTB200_RESAMPLE_NONE) {
-        // fast path: one add per row on top of the cached centre index
-        const int dpix = (ky - pad) * p.in_w + (kx - pad);
-        const float* base = my.ptr + c0;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const bool ok = g_ok && ((tap_mask[it] >> tap) & 1u);
-          v[it] = ok ? ld4(base + (long long)(pix_center[it] + dpix) * my.c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      } else {
-        // generic path: x2 up-sampling on load (the TC plans normally materialise up-sampled maps instead)
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int4 ri = rowinfo[prow + it * 32];
-          v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (g_ok && ri.w) {
-            int iy = ri.y * p.stride + ky - pad, ix = ri.z * p.stride + kx - pad;
-            v[it] = load_input4(my, ri.x, iy, ix, p.in_h, p.in_w, c0);
-          }
-        }
-      }
-    };
-
     int stage = 0, phase = 0;
-    float4 cur[4], nxt[4];
-    gather(kb_begin, cur);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      // software pipeline: the next K block's global loads are in flight while this one is split and stored
-      if (kb + 1 < num_kb) gather(kb_begin + kb + 1, nxt);
-      mbar_wait(&empty[stage], phase ^ 1);
-      uint8_t* a_big = stage_base + stage * Cfg::kStageBytes;
-      uint8_t* a_small = a_big + kATileBytes;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
+      int m_tile, n_tile, kb_begin, num_kb, split;
+      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
+      // per-row state for this tile: centre-tap pixel index, tap validity mask (zero padding), batch / coords for the
+      // generic (resampled) path
+      int pix_center[4], rb[4], ry[4], rx[4];
+      uint32_t tap_mask[4];
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const float4 v = cur[it];
-        float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
-        float4 small = make_float4(v.x - big.x, v.y - big.y, v.z - big.z, v.w - big.w);
-        *reinterpret_cast<float4*>(a_big + soff[it]) = big;
-        *reinterpret_cast<float4*>(a_small + soff[it]) = small;
+        const long long m = (long long)m_tile * kBM + prow + it * 32;
+        uint32_t mask = 0;
+        int bb = 0, oy = 0, ox = 0;
+        if (m < m_total) {
+          bb = (int)(m / hw);
+          int r = (int)(m - (long long)bb * hw);
+          oy = r / p.out_w;
+          ox = r - oy * p.out_w;
+          const int cy = oy * p.stride, cx = ox * p.stride;
+          for (int t = 0; t < taps; ++t) {
+            int iy = cy + t / p.ksize - pad, ix = cx + t % p.ksize - pad;
+            if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) mask |= 1u << t;
+          }
+        }
+        rb[it] = bb, ry[it] = oy, rx[it] = ox;
+        pix_center[it] = (bb * p.in_h + oy * p.stride) * p.in_w + ox * p.stride;
+        tap_mask[it] = mask;
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[stage]);
-      if (++stage == Cfg::kStages) {
-        stage = 0;
-        phase ^= 1;
+      // group cursor of this thread's chunk: (tap, group-in-tap), advanced by 4 groups per K block
+      int g_tap, g_r;
+      {
+        const int g = kb_begin * 4 + (q >> 1);
+        g_tap = g / groups_per_tap;
+        g_r = g - g_tap * groups_per_tap;
       }
+      auto gather = [&](float4 (&v)[4]) {
+        const bool g_ok = g_tap < taps;
+        const int tap = g_ok ? g_tap : 0;
+        const int src_i = g_r < grp_end[0] ? 0 : (g_r < grp_end[1] ? 1 : 2);
+        const int base = src_i == 0 ? 0 : (src_i == 1 ? grp_end[0] : grp_end[1]);
+        const int c0 = (g_r - base) * 8 + (q & 1) * 4;
+        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+        SrcView my = sv[0];
+        if (src_i == 1) my = sv[1];
+        if (src_i == 2) my = sv[2];
+        if (my.resample == DTB200_RESAMPLE_NONE) {
+          const int dpix = (ky - pad) * p.in_w + (kx - pad);
+          const float* bp = my.ptr + c0;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
+          for (int it = 0; it < 4; ++it) {
+            const bool ok = g_ok && ((tap_mask[it] >> tap) & 1u);
+            const long long off = ok ? (long long)(pix_center[it] + dpix) * my.c : 0;
+            float4 t = ld4(bp + off);  // always in bounds (offset 0 when masked): no branch around the load
+            v[it] = ok ? t : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g_ok && tap_mask[it] != 0u) {  // row is live; load_input4 zero-pads
+              int iy = ry[it] * p.stride + ky - pad, ix = rx[it] * p.stride + kx - pad;
+              v[it] = load_input4(my, rb[it], iy, ix, p.in_h, p.in_w, c0);
+            }
+          }
+        }
+        g_r += 4;
+        while (g_r >= groups_per_tap) g_r -= groups_per_tap, ++g_tap;
+      };
+
+      float4 cur[4], nxt[4];
+      gather(cur);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (kb + 1 < num_kb) gather(nxt);  // next K block's loads fly while this one is split and stored
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        uint8_t* a_big = a_ring + stage * kAStageBytes;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const float4 v = cur[it];
+          float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
+          float4 small = make_float4(v.x - big.x, v.y - big.y, v.z - big.z, v.w - big.w);
+          *reinterpret_cast<float4*>(a_big + soff[it]) = big;
+          *reinterpret_cast<float4*>(a_big + kATileBytes + soff[it]) = small;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[stage]);
+        if (++stage == Cfg::kAStages) stage = 0, phase ^= 1;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
+      }
     }
-    // ============================================================ epilogue (same warps)
-    mbar_wait(accum, 0);
-    tc_fence_after();
-    const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row; warps 0-3 / 4-7 split the columns
-    const int4 ri = rowinfo[row];
-    constexpr int kColsPerHalf = BN / 2;
-    const int col0 = (warp >> 2) * kColsPerHalf;
-    const int n_base = n_tile * BN;
-    float* dst = p.dst + (((long long)ri.x * p.out_h + ri.y) * p.out_w + ri.z) * p.out_c + n_base;
-    const float* res = p.residual ? p.residual + (((long long)ri.x * p.out_h + ri.y) * p.out_w + ri.z) * p.out_c + n_base : nullptr;
-#pragma unroll
-    for (int cc = 0; cc < kColsPerHalf; cc += 32) {
-      float v[32];
-      tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col0 + cc), v);
+  } else if (warp < kMmaWarp) {
+    // ============================================================ epilogue warps
+    const int ew = warp - kProducerWarps;  // == warp % 4: TMEM lane quadrant
+    const int row = ew * 32 + lane;
+    int use = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
+      int m_tile, n_tile, kb_begin, num_kb, split;
+      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
+      const int buf = use & 1;
+      const long long m = (long long)m_tile * kBM + row;
+      const bool live = m < m_total;
+      const int n_base = n_tile * BN;
+      mbar_wait(&acc_full[buf], (use >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(ew * 32) << 16);
+      float* dst = nullptr;
+      const float* res = nullptr;
       if (partial) {
-        // split-K: raw fp32 partial sums -> workspace[split][m][out_c]; bias/residual/activation happen in the reducer
-        if (ri.w) {
-          float* w = partial + ((long long)blockIdx.z * m_total + (m0 + row)) * p.out_c + n_base + col0 + cc;
+        dst = partial + ((long long)split * m_total + m) * p.out_c + n_base;
+      } else {
+        dst = p.dst + m * p.out_c + n_base;                 // NHWC: pixel index m is the row index
+        res = p.residual ? p.residual + m * p.out_c + n_base : nullptr;
+      }
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)cc, v);
+        if (!live) continue;
+        if (partial) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(w + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-      } else if (ri.w) {
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = col0 + cc + j;
-          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (p.bias) {
-            float4 bb = ld4(p.bias + n_base + n);
-            o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
+          for (int j = 0; j < 32; j += 4) {
+            const int n = cc + j;
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.bias) {
+              float4 bb = ld4(p.bias + n_base + n);
+              o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
+            }
+            if (res) {
+              float4 rr = ld4(res + n);
+              o.x += rr.x, o.y += rr.y, o.z += rr.z, o.w += rr.w;
+            }
+            o.x = activate(o.x, p.act, p.act_slope);
+            o.y = activate(o.y, p.act, p.act_slope);
+            o.z = activate(o.z, p.act, p.act_slope);
+            o.w = activate(o.w, p.act, p.act_slope);
+            *reinterpret_cast<float4*>(dst + n) = o;
           }
-          if (res) {
-            float4 rr = ld4(res + n);
-            o.x += rr.x, o.y += rr.y, o.z += rr.z, o.w += rr.w;
-          }
-          o.x = activate(o.x, p.act, p.act_slope);
-          o.y = activate(o.y, p.act, p.act_slope);
-          o.z = activate(o.z, p.act, p.act_slope);
-          o.w = activate(o.w, p.act, p.act_slope);
-          *reinterpret_cast<float4*>(dst + n) = o;
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-    tc_fence_before();
-  } else {
-    // ============================================================ weight loader + MMA issuer (one lane)
+  } else if (warp == kMmaWarp) {
+    // ============================================================ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
-      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) +
-                             ((size_t)n_tile * num_kb_total + kb_begin) * (2 * Cfg::kBTileBytes);
-      int stage = 0, phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        uint8_t* a_big = stage_base + stage * Cfg::kStageBytes;
-        uint8_t* b_big = a_big + 2 * kATileBytes;
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kBTileBytes);
-        bulk_g2s(b_big, wbase + (size_t)kb * (2 * Cfg::kBTileBytes), 2 * Cfg::kBTileBytes, &full[stage]);
-        mbar_wait(&full[stage], phase);
+      int sa = 0, pa = 0, sb = 0, pb = 0, use = 0;
+      for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
+        int m_tile, n_tile, kb_begin, num_kb, split;
+        decode(item, m_tile, n_tile, kb_begin, num_kb, split);
+        const int buf = use & 1;
+        mbar_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_big_u = smem_u32(a_big), a_small_u = a_big_u + kATileBytes;
-        const uint32_t b_big_u = a_big_u + 2 * kATileBytes, b_small_u = b_big_u + Cfg::kBTileBytes;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&a_full[sa], pa);
+          mbar_wait(&b_full[sb], pb);
+          tc_fence_after();
+          const uint32_t a_big_u = smem_u32(a_ring + sa * kAStageBytes), a_small_u = a_big_u + kATileBytes;
+          const uint32_t b_big_u = smem_u32(b_ring + sb * Cfg::kBStageBytes), b_small_u = b_big_u + BN * 128;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes along K inside the swizzled row
-          const uint64_t da_b = umma_desc_k128(a_big_u + ko), da_s = umma_desc_k128(a_small_u + ko);
-          const uint64_t db_b = umma_desc_k128(b_big_u + ko), db_s = umma_desc_k128(b_small_u + ko);
-          umma_tf32(tmem_d, da_s, db_b, idesc, (kb | ks) != 0);
-          umma_tf32(tmem_d, da_b, db_s, idesc, true);
-          umma_tf32(tmem_d, da_b, db_b, idesc, true);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes along K inside the swizzled row
+            const uint64_t da_b = umma_desc_k128(a_big_u + ko), da_s = umma_desc_k128(a_small_u + ko);
+            const uint64_t db_b = umma_desc_k128(b_big_u + ko), db_s = umma_desc_k128(b_small_u + ko);
+            umma_tf32(tmem_d, da_s, db_b, idesc, (kb | ks) != 0);
+            umma_tf32(tmem_d, da_b, db_s, idesc, true);
+            umma_tf32(tmem_d, da_b, db_b, idesc, true);
+          }
+          umma_commit(&a_empty[sa]);
+          umma_commit(&b_empty[sb]);
+          if (++sa == Cfg::kAStages) sa = 0, pa ^= 1;
+          if (++sb == Cfg::kBStages) sb = 0, pb ^= 1;
         }
-        umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
-        if (++stage == Cfg::kStages) {
-          stage = 0;
-          phase ^= 1;
+        umma_commit(&acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================================================ weight-tile loader
+    if (lane == 0) {
+      int sb = 0, pb = 0;
+      for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
+        int m_tile, n_tile, kb_begin, num_kb, split;
+        decode(item, m_tile, n_tile, kb_begin, num_kb, split);
+        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) +
+                               ((size_t)n_tile * wk.num_kb_total + kb_begin) * Cfg::kBStageBytes;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&b_empty[sb], pb ^ 1);
+          mbar_arrive_expect_tx(&b_full[sb], Cfg::kBStageBytes);
+          bulk_g2s(b_ring + sb * Cfg::kBStageBytes, wbase + (size_t)kb * Cfg::kBStageBytes, Cfg::kBStageBytes, &b_full[sb]);
+          if (++sb == Cfg::kBStages) sb = 0, pb ^= 1;
         }
       }
-      umma_commit(accum);  // accumulator complete
     }
     __syncwarp();
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == kProducerWarps) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_d);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -422,18 +473,31 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
                   (long long)need);
     partial = reinterpret_cast<float*>(p.workspace);
   }
-  const int kb_per_split = (num_kb + splits - 1) / splits;
-  const int zsplits = (num_kb + kb_per_split - 1) / kb_per_split;
-  dim3 grid((unsigned)((m_total + kBM - 1) / kBM), p.out_c / bn, zsplits);
+  TcWork wk;
+  wk.num_kb_total = num_kb;
+  wk.kb_per_split = (num_kb + splits - 1) / splits;
+  wk.splits = (num_kb + wk.kb_per_split - 1) / wk.kb_per_split;
+  wk.m_tiles = (int)((m_total + kBM - 1) / kBM);
+  wk.n_tiles = p.out_c / bn;
+  wk.total = (long long)wk.m_tiles * wk.n_tiles * wk.splits;
+  const int zsplits = wk.splits;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const unsigned grid = (unsigned)(wk.total < num_sms ? wk.total : num_sms);
   cudaError_t e;
   if (bn == 128) {
     e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes);
     if (e != cudaSuccess) return fail(DTB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    conv_tc_kernel<128><<<grid, kThreads, TcCfg<128>::kSmemBytes, stream>>>(p, in_c_total, m_total, num_kb, kb_per_split, partial);
+    conv_tc_kernel<128><<<grid, kThreads, TcCfg<128>::kSmemBytes, stream>>>(p, in_c_total, m_total, wk, partial);
   } else {
     e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes);
     if (e != cudaSuccess) return fail(DTB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    conv_tc_kernel<64><<<grid, kThreads, TcCfg<64>::kSmemBytes, stream>>>(p, in_c_total, m_total, num_kb, kb_per_split, partial);
+    conv_tc_kernel<64><<<grid, kThreads, TcCfg<64>::kSmemBytes, stream>>>(p, in_c_total, m_total, wk, partial);
   }
   int rc = check_launch("conv_tc_kernel");
   if (rc != DTB200_OK || !partial) return rc;

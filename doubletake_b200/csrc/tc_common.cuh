@@ -34,6 +34,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
+    if (spin > 4) __nanosleep(40);  // back off: waiting warps must not steal issue slots from working ones
     if ((spin & 0xFFF) == 0xFFF) {
       long long now = clock64();
       if (t0 == 0) t0 = now;
