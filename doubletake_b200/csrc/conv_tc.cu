@@ -37,8 +37,9 @@ constexpr int kAStageBytes = 2 * kATileBytes;
 template <int BN>
 struct TcCfg {
   static constexpr int kBStageBytes = 2 * BN * 128;  // B_big | B_small
-  static constexpr int kAStages = BN <= 64 ? 4 : 3;
-  static constexpr int kBStages = BN <= 64 ? 4 : 3;
+  static constexpr int kAStages = BN <= 64 ? 5 : 4;
+  static constexpr int kBStages = 3;
+  static constexpr int kDepth = kAStages - 1;      // K blocks of cp.async in flight per producer thread
   static constexpr int kTmemCols = 2 * BN;           // two accumulators
   static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
@@ -158,7 +159,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         g_tap = g / groups_per_tap;
         g_r = g - g_tap * groups_per_tap;
       }
-      auto gather = [&](float4 (&v)[4]) {
+      // Issue this thread's 4 chunks of the next K block into stage `st`: raw fp32 by cp.async straight into the
+      // swizzled A_big tile (zero-fill for padding); resampled sources go through registers.
+      auto issue = [&](int st) {
         const bool g_ok = g_tap < taps;
         const int tap = g_ok ? g_tap : 0;
         const int src_i = g_r < grp_end[0] ? 0 : (g_r < grp_end[1] ? 1 : 2);
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         SrcView my = sv[0];
         if (src_i == 1) my = sv[1];
         if (src_i == 2) my = sv[2];
+        uint8_t* a_big = a_ring + st * kAStageBytes;
         if (my.resample == DTB200_RESAMPLE_NONE) {
           const int dpix = (ky - pad) * p.in_w + (kx - pad);
           const float* bp = my.ptr + c0;
@@ -175,32 +179,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
           for (int it = 0; it < 4; ++it) {
             const bool ok = g_ok && ((tap_mask[it] >> tap) & 1u);
             const long long off = ok ? (long long)(pix_center[it] + dpix) * my.c : 0;
-            float4 t = ld4(bp + off);  // always in bounds (offset 0 when masked): no branch around the load
-            v[it] = ok ? t : make_float4(0.f, 0.f, 0.f, 0.f);
+            cp_async16(a_big + soff[it], bp + off, ok ? 16u : 0u);
           }
         } else {
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
-            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g_ok && tap_mask[it] != 0u) {  // row is live; load_input4 zero-pads
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g_ok && tap_mask[it] != 0u) {
               int iy = ry[it] * p.stride + ky - pad, ix = rx[it] * p.stride + kx - pad;
-              v[it] = load_input4(my, rb[it], iy, ix, p.in_h, p.in_w, c0);
+              v = load_input4(my, rb[it], iy, ix, p.in_h, p.in_w, c0);
             }
+            *reinterpret_cast<float4*>(a_big + soff[it]) = v;
           }
         }
         g_r += 4;
         while (g_r >= groups_per_tap) g_r -= groups_per_tap, ++g_tap;
       };
 
-      float4 cur[4], nxt[4];
-      gather(cur);
+      // prologue: kDepth K blocks in flight
+      int issue_stage = stage, issue_phase = phase;
+#pragma unroll 1
+      for (int i = 0; i < Cfg::kDepth; ++i) {
+        if (i < num_kb) {
+          mbar_wait(&a_empty[issue_stage], issue_phase ^ 1);
+          issue(issue_stage);
+          if (++issue_stage == Cfg::kAStages) issue_stage = 0, issue_phase ^= 1;
+        }
+        cp_async_commit();
+      }
+#pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
-        if (kb + 1 < num_kb) gather(nxt);  // next K block's loads fly while this one is split and stored
-        mbar_wait(&a_empty[stage], phase ^ 1);
+        cp_async_wait<Cfg::kDepth - 1>();  // this thread's chunks of K block kb have landed
         uint8_t* a_big = a_ring + stage * kAStageBytes;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const float4 v = cur[it];
+          const float4 v = *reinterpret_cast<const float4*>(a_big + soff[it]);
           float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
           float4 small = make_float4(v.x - big.x, v.y - big.y, v.z - big.z, v.w - big.w);
           *reinterpret_cast<float4*>(a_big + soff[it]) = big;
@@ -210,9 +223,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[stage]);
         if (++stage == Cfg::kAStages) stage = 0, phase ^= 1;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
+        if (kb + Cfg::kDepth < num_kb) {
+          mbar_wait(&a_empty[issue_stage], issue_phase ^ 1);
+          issue(issue_stage);
+          if (++issue_stage == Cfg::kAStages) issue_stage = 0, issue_phase ^= 1;
+        }
+        cp_async_commit();
       }
+      cp_async_wait<0>();
     }
   } else if (warp < kMmaWarp) {
     // ============================================================ epilogue warps

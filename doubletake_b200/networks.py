@@ -59,7 +59,7 @@ class ConvPlan:
         return f
 
     def _pack(self, weight):
-        key = id(weight)
+        key = weight.data_ptr()
         if key not in self._packed:
             w = L.f32(weight.detach(), self.device)
             oc, ic, k, _ = w.shape
@@ -72,7 +72,7 @@ class ConvPlan:
 
     def upsampled(self, f: Feature, mode):
         """Materialise the x2 up-sampled map once (resample descriptor, ksize = 0) and share it between consumers."""
-        key = (id(f), mode)
+        key = (f.t.data_ptr(), mode)  # buffers live as long as the plan (self.keep), so the pointer is a stable key
         if key not in self._upsampled:
             out = self.new(f.b, 2 * f.h, 2 * f.w, f.c)
             op = L.ConvParams()
