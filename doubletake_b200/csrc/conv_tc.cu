@@ -26,7 +26,9 @@ using namespace tc;
 
 constexpr int kBM = 128;                 // pixels per tile (UMMA M)
 constexpr int kBK = 32;                  // fp32 per K block = one 128-byte swizzled row
-constexpr int kProducerWarps = 8;
+constexpr int kLoadWarps = 4;            // cp.async im2col gather (never fence: they keep many loads in flight)
+constexpr int kSplitWarps = 4;           // smem-only 3xTF32 split + proxy fence
+constexpr int kProducerWarps = kLoadWarps + kSplitWarps;
 constexpr int kEpilogueWarps = 4;
 constexpr int kMmaWarp = kProducerWarps + kEpilogueWarps;      // 12
 constexpr int kLoaderWarp = kMmaWarp + 1;                      // 13
@@ -39,9 +41,9 @@ struct TcCfg {
   static constexpr int kBStageBytes = 2 * BN * 128;  // B_big | B_small
   static constexpr int kAStages = BN <= 64 ? 5 : 4;
   static constexpr int kBStages = 3;
-  static constexpr int kDepth = kAStages - 1;      // K blocks of cp.async in flight per producer thread
+
   static constexpr int kTmemCols = 2 * BN;           // two accumulators
-  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 /*align*/ + 1024 /*barriers*/;
 };
 
 __host__ __device__ inline int tc_num_kblocks(int in_c, int ksize) { return (in_c * ksize * ksize + kBK - 1) / kBK; }
@@ -66,8 +68,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + Cfg::kAStages * kAStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + Cfg::kBStages * Cfg::kBStageBytes);
-  uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + Cfg::kAStages;
+  uint64_t* raw_full = bars;                      // loaders -> splitters (cp.async completion)
+  uint64_t* a_full = raw_full + Cfg::kAStages;    // splitters -> MMA
+  uint64_t* a_empty = a_full + Cfg::kAStages;     // MMA -> loaders
   uint64_t* b_full = a_empty + Cfg::kAStages;
   uint64_t* b_empty = b_full + Cfg::kBStages;
   uint64_t* acc_full = b_empty + Cfg::kBStages;   // [2]
@@ -76,7 +79,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < Cfg::kAStages; ++s) mbar_init(&a_full[s], kProducerWarps), mbar_init(&a_empty[s], 1);
+    for (int s = 0; s < Cfg::kAStages; ++s)
+      mbar_init(&raw_full[s], kLoadWarps * 32), mbar_init(&a_full[s], kSplitWarps), mbar_init(&a_empty[s], 1);
     for (int s = 0; s < Cfg::kBStages; ++s) mbar_init(&b_full[s], 1), mbar_init(&b_empty[s], 1);
     for (int s = 0; s < 2; ++s) mbar_init(&acc_full[s], 1), mbar_init(&acc_empty[s], kEpilogueWarps);
     fence_mbar_init();
@@ -97,8 +101,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
     num_kb = min(wk.kb_per_split, wk.num_kb_total - kb_begin);
   };
 
-  if (warp < kProducerWarps) {
-    // ============================================================ A producers
+  if (warp < kLoadWarps) {
+    // ============================================================ A loaders: raw fp32 im2col rows by cp.async
     SrcView sv[DTB200_CONV_MAX_SRC];
     int grp_end[DTB200_CONV_MAX_SRC];
     int acc_g = 0;
@@ -117,39 +121,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
     const int taps = p.ksize * p.ksize;
     const int pad = p.ksize / 2;
     const int q = tid & 7;          // 16-byte chunk of the 128-byte row this thread fills
-    const int prow = tid >> 3;      // rows prow, prow+32, prow+64, prow+96
-    uint32_t soff[4];
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int row = prow + it * 32;
-      soff[it] = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
-    }
+    const int prow = tid >> 3;      // rows prow + 16*it, it = 0..7
     int stage = 0, phase = 0;
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
       int m_tile, n_tile, kb_begin, num_kb, split;
       decode(item, m_tile, n_tile, kb_begin, num_kb, split);
-      // per-row state for this tile: centre-tap pixel index, tap validity mask (zero padding), batch / coords for the
-      // generic (resampled) path
-      int pix_center[4], rb[4], ry[4], rx[4];
-      uint32_t tap_mask[4];
+      // per-row state for this tile: centre-tap pixel index and tap validity mask (zero padding)
+      int pix_center[8];
+      uint32_t tap_mask[8];
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const long long m = (long long)m_tile * kBM + prow + it * 32;
+      for (int it = 0; it < 8; ++it) {
+        const long long m = (long long)m_tile * kBM + prow + it * 16;
         uint32_t mask = 0;
-        int bb = 0, oy = 0, ox = 0;
+        int pc = 0;
         if (m < m_total) {
-          bb = (int)(m / hw);
-          int r = (int)(m - (long long)bb * hw);
-          oy = r / p.out_w;
-          ox = r - oy * p.out_w;
+          const int bb = (int)(m / hw);
+          const int r = (int)(m - (long long)bb * hw);
+          const int oy = r / p.out_w, ox = r - oy * p.out_w;
           const int cy = oy * p.stride, cx = ox * p.stride;
           for (int t = 0; t < taps; ++t) {
             int iy = cy + t / p.ksize - pad, ix = cx + t % p.ksize - pad;
             if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) mask |= 1u << t;
           }
+          pc = (bb * p.in_h + cy) * p.in_w + cx;
         }
-        rb[it] = bb, ry[it] = oy, rx[it] = ox;
-        pix_center[it] = (bb * p.in_h + oy * p.stride) * p.in_w + ox * p.stride;
+        pix_center[it] = pc;
         tap_mask[it] = mask;
       }
       // group cursor of this thread's chunk: (tap, group-in-tap), advanced by 4 groups per K block
@@ -159,9 +155,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         g_tap = g / groups_per_tap;
         g_r = g - g_tap * groups_per_tap;
       }
-      // Issue this thread's 4 chunks of the next K block into stage `st`: raw fp32 by cp.async straight into the
-      // swizzled A_big tile (zero-fill for padding); resampled sources go through registers.
-      auto issue = [&](int st) {
+#pragma unroll 1
+      for (int kb = 0; kb < num_kb; ++kb) {
         const bool g_ok = g_tap < taps;
         const int tap = g_ok ? g_tap : 0;
         const int src_i = g_r < grp_end[0] ? 0 : (g_r < grp_end[1] ? 1 : 2);
@@ -171,48 +166,61 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         SrcView my = sv[0];
         if (src_i == 1) my = sv[1];
         if (src_i == 2) my = sv[2];
-        uint8_t* a_big = a_ring + st * kAStageBytes;
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        uint8_t* a_big = a_ring + stage * kAStageBytes;
         if (my.resample == DTB200_RESAMPLE_NONE) {
           const int dpix = (ky - pad) * p.in_w + (kx - pad);
           const float* bp = my.ptr + c0;
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
+          for (int it = 0; it < 8; ++it) {
+            const int row = prow + it * 16;
             const bool ok = g_ok && ((tap_mask[it] >> tap) & 1u);
             const long long off = ok ? (long long)(pix_center[it] + dpix) * my.c : 0;
-            cp_async16(a_big + soff[it], bp + off, ok ? 16u : 0u);
+            cp_async16(a_big + (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4), bp + off, ok ? 16u : 0u);
           }
         } else {
+          // generic path: x2 up-sampling on load (the TC plans normally materialise up-sampled maps instead)
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
+          for (int it = 0; it < 8; ++it) {
+            const int row = prow + it * 16;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (g_ok && tap_mask[it] != 0u) {
-              int iy = ry[it] * p.stride + ky - pad, ix = rx[it] * p.stride + kx - pad;
-              v = load_input4(my, rb[it], iy, ix, p.in_h, p.in_w, c0);
+              const long long m = (long long)m_tile * kBM + row;
+              const int bb = (int)(m / hw);
+              const int r = (int)(m - (long long)bb * hw);
+              const int oy = r / p.out_w, ox = r - oy * p.out_w;
+              v = load_input4(my, bb, oy * p.stride + ky - pad, ox * p.stride + kx - pad, p.in_h, p.in_w, c0);
             }
-            *reinterpret_cast<float4*>(a_big + soff[it]) = v;
+            *reinterpret_cast<float4*>(a_big + (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4)) = v;
           }
+          __threadfence_block();
         }
+        cp_async_mbar_arrive(&raw_full[stage]);  // fires when this thread's copies have landed; the thread moves on
+        if (++stage == Cfg::kAStages) stage = 0, phase ^= 1;
         g_r += 4;
         while (g_r >= groups_per_tap) g_r -= groups_per_tap, ++g_tap;
-      };
-
-      // prologue: kDepth K blocks in flight
-      int issue_stage = stage, issue_phase = phase;
-#pragma unroll 1
-      for (int i = 0; i < Cfg::kDepth; ++i) {
-        if (i < num_kb) {
-          mbar_wait(&a_empty[issue_stage], issue_phase ^ 1);
-          issue(issue_stage);
-          if (++issue_stage == Cfg::kAStages) issue_stage = 0, issue_phase ^= 1;
-        }
-        cp_async_commit();
       }
+    }
+  } else if (warp < kProducerWarps) {
+    // ============================================================ A splitters: raw -> (big, small), shared memory only
+    const int st = tid - kLoadWarps * 32;
+    const int q = st & 7, prow = st >> 3;
+    uint32_t soff[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = prow + it * 16;
+      soff[it] = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
+    }
+    int stage = 0, phase = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
+      int m_tile, n_tile, kb_begin, num_kb, split;
+      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
 #pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
-        cp_async_wait<Cfg::kDepth - 1>();  // this thread's chunks of K block kb have landed
+        mbar_wait(&raw_full[stage], phase);
         uint8_t* a_big = a_ring + stage * kAStageBytes;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
+        for (int it = 0; it < 8; ++it) {
           const float4 v = *reinterpret_cast<const float4*>(a_big + soff[it]);
           float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
           float4 small = make_float4(v.x - big.x, v.y - big.y, v.z - big.z, v.w - big.w);
@@ -223,18 +231,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[stage]);
         if (++stage == Cfg::kAStages) stage = 0, phase ^= 1;
-        if (kb + Cfg::kDepth < num_kb) {
-          mbar_wait(&a_empty[issue_stage], issue_phase ^ 1);
-          issue(issue_stage);
-          if (++issue_stage == Cfg::kAStages) issue_stage = 0, issue_phase ^= 1;
-        }
-        cp_async_commit();
       }
-      cp_async_wait<0>();
     }
   } else if (warp < kMmaWarp) {
     // ============================================================ epilogue warps
-    const int ew = warp - kProducerWarps;  // == warp % 4: TMEM lane quadrant
+    const int ew = warp - kProducerWarps;  // == warp % 4 (kProducerWarps is a multiple of 4): TMEM lane quadrant
     const int row = ew * 32 + lane;
     int use = 0;
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
