@@ -290,23 +290,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   } else if (warp == kMmaWarp) {
-    // ============================================================ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
-      int sa = 0, pa = 0, sb = 0, pb = 0, use = 0;
-      for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
-        int m_tile, n_tile, kb_begin, num_kb, split;
-        decode(item, m_tile, n_tile, kb_begin, num_kb, split);
-        const int buf = use & 1;
-        mbar_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+    // ============================================================ MMA issuer (whole warp convergent; elect.sync issues)
+    constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
+    int sa = 0, pa = 0, sb = 0, pb = 0, use = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
+      int m_tile, n_tile, kb_begin, num_kb, split;
+      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
+      const int buf = use & 1;
+      mbar_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_u + (uint32_t)(buf * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&a_full[sa], pa);
+        mbar_wait(&b_full[sb], pb);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&a_full[sa], pa);
-          mbar_wait(&b_full[sb], pb);
-          tc_fence_after();
-          const uint32_t a_big_u = smem_u32(a_ring + sa * kAStageBytes), a_small_u = a_big_u + kATileBytes;
-          const uint32_t b_big_u = smem_u32(b_ring + sb * Cfg::kBStageBytes), b_small_u = b_big_u + BN * 128;
+        const uint32_t a_big_u = a_ring_u + sa * kAStageBytes, a_small_u = a_big_u + kATileBytes;
+        const uint32_t b_big_u = b_ring_u + sb * Cfg::kBStageBytes, b_small_u = b_big_u + BN * 128;
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes along K inside the swizzled row
@@ -318,31 +320,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
           }
           umma_commit(&a_empty[sa]);
           umma_commit(&b_empty[sb]);
-          if (++sa == Cfg::kAStages) sa = 0, pa ^= 1;
-          if (++sb == Cfg::kBStages) sb = 0, pb ^= 1;
         }
-        umma_commit(&acc_full[buf]);
+        __syncwarp();
+        if (++sa == Cfg::kAStages) sa = 0, pa ^= 1;
+        if (++sb == Cfg::kBStages) sb = 0, pb ^= 1;
       }
+      if (elect_one()) umma_commit(&acc_full[buf]);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
-    // ============================================================ weight-tile loader
-    if (lane == 0) {
-      int sb = 0, pb = 0;
-      for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
-        int m_tile, n_tile, kb_begin, num_kb, split;
-        decode(item, m_tile, n_tile, kb_begin, num_kb, split);
-        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) +
-                               ((size_t)n_tile * wk.num_kb_total + kb_begin) * Cfg::kBStageBytes;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&b_empty[sb], pb ^ 1);
+    // ============================================================ weight-tile loader (whole warp convergent)
+    int sb = 0, pb = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
+      int m_tile, n_tile, kb_begin, num_kb, split;
+      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) +
+                             ((size_t)n_tile * wk.num_kb_total + kb_begin) * Cfg::kBStageBytes;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&b_empty[sb], pb ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&b_full[sb], Cfg::kBStageBytes);
           bulk_g2s(b_ring + sb * Cfg::kBStageBytes, wbase + (size_t)kb * Cfg::kBStageBytes, Cfg::kBStageBytes, &b_full[sb]);
-          if (++sb == Cfg::kBStages) sb = 0, pb ^= 1;
         }
+        __syncwarp();
+        if (++sb == Cfg::kBStages) sb = 0, pb ^= 1;
       }
     }
-    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();

@@ -374,24 +374,28 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
     }
   } else {
     // ================================================================================ weight copies + MMA issue
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(kTRows, kTHidden);
-      int stage = 0, phase = 0;
-      for (int iter = 0; iter < num_iters; ++iter) {
-        for (int u = 0; u < nkb; ++u) {
-          uint8_t* a_big = stages + stage * kTStage;
-          uint8_t* b_big = a_big + 2 * kTATile;
-          const uint8_t* wsrc = (u < nkb1) ? reinterpret_cast<const uint8_t*>(w1p) + (size_t)u * (2 * kTBTile)
-                                           : reinterpret_cast<const uint8_t*>(w2p) + (size_t)(u - nkb1) * (2 * kTBTile);
-          mbar_wait(&empty[stage], phase ^ 1);
+    // whole warp convergent; single-thread instructions are issued under elect.sync (see tc_common.cuh)
+    constexpr uint32_t idesc = umma_idesc_tf32(kTRows, kTHidden);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t stages_u = smem_u32(stages);
+    int stage = 0, phase = 0;
+    for (int iter = 0; iter < num_iters; ++iter) {
+      for (int u = 0; u < nkb; ++u) {
+        const uint32_t a_big_u = stages_u + stage * kTStage, a_small_u = a_big_u + kTATile;
+        const uint32_t b_big_u = a_big_u + 2 * kTATile, b_small_u = b_big_u + kTBTile;
+        const uint8_t* wsrc = (u < nkb1) ? reinterpret_cast<const uint8_t*>(w1p) + (size_t)u * (2 * kTBTile)
+                                         : reinterpret_cast<const uint8_t*>(w2p) + (size_t)(u - nkb1) * (2 * kTBTile);
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full[stage], 2 * kTBTile);
-          bulk_g2s(b_big, wsrc, 2 * kTBTile, &full[stage]);
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_big_u = smem_u32(a_big), a_small_u = a_big_u + kTATile;
-          const uint32_t b_big_u = a_big_u + 2 * kTATile, b_small_u = b_big_u + kTBTile;
-          const uint32_t dst = (u < nkb1) ? tmem_d1 : tmem_d2;
-          const bool first = (u == 0) || (u == nkb1);
+          bulk_g2s(stages + stage * kTStage + 2 * kTATile, wsrc, 2 * kTBTile, &full[stage]);
+        }
+        __syncwarp();
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t dst = (u < nkb1) ? tmem_u : tmem_u + kTHidden;
+        const bool first = (u == 0) || (u == nkb1);
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t ko = ks * 32;
@@ -404,11 +408,11 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
           umma_commit(&empty[stage]);
           if (u == nkb1 - 1) umma_commit(d1_full);
           if (u == nkb - 1) umma_commit(d2_full);
-          if (++stage == kTStages) stage = 0, phase ^= 1;
         }
+        __syncwarp();
+        if (++stage == kTStages) stage = 0, phase ^= 1;
       }
     }
-    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
