@@ -55,6 +55,7 @@ class ConvParams(C.Structure):
 # every symbol include/doubletake_b200.h declares (tests/test_capi_symbols.py checks the header against this list)
 SYMBOLS = {
     "dtb200_abi_version": (C.c_int, []),
+    "dtb200_debug_set": (C.c_int, [C.c_int]),
     "dtb200_last_error": (C.c_char_p, []),
     "dtb200_launch_count": (C.c_uint64, []),
     "dtb200_nchw_to_nhwc": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),

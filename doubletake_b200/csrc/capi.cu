@@ -13,6 +13,7 @@ int launch_pack_tc(const float* oihw, float* packed, int out_c, int in_c, int ks
 uint64_t packed_floats_tc(int out_c, int in_c, int ksize);                                               // conv_tc.cu
 uint64_t conv_tc_workspace_bytes(const dtb200_conv_params& p, int in_c_total);                           // conv_tc.cu
 int launch_resample_copy(const dtb200_conv_params& p, cudaStream_t stream);                              // conv_tc.cu
+int conv_tc_debug_set(int flags);                                                                        // conv_tc.cu
 
 // (N,C,H,W) <-> (N,H,W,C): 32x32 smem tile transpose of the (C, H*W) matrix of each sample.
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
@@ -92,6 +93,7 @@ static int conv_total_in_c(const dtb200_conv_params& p, int& total) {
 
 using namespace dtb200;
 
+extern "C" int dtb200_debug_set(int flags) { return conv_tc_debug_set(flags); }
 extern "C" int dtb200_abi_version(void) { return DTB200_ABI_VERSION; }
 extern "C" const char* dtb200_last_error(void) { return g_error; }
 extern "C" uint64_t dtb200_launch_count(void) { return g_launches.load(); }

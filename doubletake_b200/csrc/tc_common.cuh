@@ -46,8 +46,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
-    if (done) return;
-    if (spin > 4) __nanosleep(40);  // back off: waiting warps must not steal issue slots from working ones
+    if (done) return;  // try_wait suspends the thread in hardware until the phase flips or a short time limit expires
     if ((spin & 0xFFF) == 0xFFF) {
       long long now = clock64();
       if (t0 == 0) t0 = now;

@@ -33,6 +33,8 @@ typedef void* dtb200_stream_t; /* cudaStream_t */
 #define DTB200_MAX_VIEWS 16
 
 int dtb200_abi_version(void);
+/* development only: knock-out switches for the tensor-core conv pipeline (0 = normal operation) */
+int dtb200_debug_set(int flags);
 const char* dtb200_last_error(void);
 /* number of kernels this library has launched from the calling process (bench.py's gpu_launches claim) */
 uint64_t dtb200_launch_count(void);
