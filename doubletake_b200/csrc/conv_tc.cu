@@ -58,15 +58,15 @@ struct TcWork {  // persistent tile scheduler: item -> (m tile, n tile, K split)
 };
 
 // Persistent warp-specialised implicit-GEMM conv.  One CTA per SM loops over work items (static stride).
-//   warps 0-3   A loaders: raw fp32 im2col rows by cp.async (zero-fill = padding) into the swizzled A_big tile; completion is
+//   warps 0-3   A loaders (warp w owns stage w; warps >= kStages idle): raw fp32 im2col rows by cp.async (zero-fill = padding) into the swizzled A_big tile; completion is
 //               signalled by the hardware (cp.async.mbarrier.arrive.noinc), the warp never fences and never waits on data
 //   warps 4-7   A splitters: A_big (raw) -> tf32-truncated big in place + small = x - big; fence.proxy.async; arrive
 //   warps 8-11  epilogue: TMEM -> bias/residual/activation -> NHWC store (or split-K partials); double-buffered accumulator
 //   warp 12     MMA issuer (convergent warp, elect.sync): 12 tcgen05.mma per K block, tcgen05.commit frees the stage
 //   warp 13     weight tiles by cp.async.bulk into the same stage/barrier as A, plus next tile's row info (pixel index and
 //               zero-padding tap mask of the 128 rows) so the loaders start every tile without a prologue
-// Loader / splitter warp w owns K blocks w, w+4, ... so four K blocks are in flight per role; all roles derive
-// (stage, phase) of a K block from its global sequence number.
+// Loader / splitter warp w owns the K blocks whose global sequence number n has n % kStages == w (always stage w), so
+// kStages K blocks are in flight per role and every waiter observes each phase of its barriers in order.
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_params p, int in_c_total, long long m_total,
                                                               TcWork wk, float* __restrict__ partial) {
@@ -139,17 +139,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       int m_tile, n_tile, kb_begin, num_kb, split;
       decode(item, m_tile, n_tile, kb_begin, num_kb, split);
       const int rb = use & 1;
-      mbar_wait(&ri_full[rb], (use >> 1) & 1);
+      mbar_wait(&ri_full[rb], (use >> 1) & 1, 100 + rb);
       const int2* ri = rowinfo + rb * kBM;
-      // group cursor of this lane's chunk for this warp's first K block; advanced by 16 groups (4 K blocks) per step
+      // Ownership by GLOBAL sequence number: warp w owns the K blocks with n % S == w, i.e. always stage w, so it observes
+      // every phase of its stage's barriers in order (a parity wait must never skip a phase).  Warps >= S idle.
+      const int kb0 = warp < S ? (int)(((warp - (int)(kcount % S)) + S) % S) : num_kb;
       int g_tap, g_r;
       {
-        const int g = (kb_begin + warp) * 4 + (q >> 1);
+        const int g = (kb_begin + kb0) * 4 + (q >> 1);
         g_tap = g / groups_per_tap;
         g_r = g - g_tap * groups_per_tap;
       }
 #pragma unroll 1
-      for (int kb = warp; kb < num_kb; kb += kLoadWarps) {
+      for (int kb = kb0; kb < num_kb; kb += S) {
         const long long n = kcount + kb;
         const int stage = (int)(n % S), phase = (int)((n / S) & 1);
         const bool g_ok = g_tap < taps;
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         SrcView my = sv[0];
         if (src_i == 1) my = sv[1];
         if (src_i == 2) my = sv[2];
-        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_wait(&empty[stage], phase ^ 1, 200 + stage + 10 * (int)(n & 7));
         uint8_t* a_big = ring + stage * Cfg::kStageBytes;
         if (dbg & kDbgNoLoads) {
         } else if (my.resample == DTB200_RESAMPLE_NONE) {
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
           __threadfence_block();
         }
         cp_async_mbar_arrive(&raw_full[stage]);  // fires when this lane's copies have landed; the warp moves on
-        g_r += 4 * kLoadWarps;
+        g_r += 4 * S;
         while (g_r >= groups_per_tap) g_r -= groups_per_tap, ++g_tap;
       }
       kcount += num_kb;
@@ -209,11 +211,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
       int m_tile, n_tile, kb_begin, num_kb, split;
       decode(item, m_tile, n_tile, kb_begin, num_kb, split);
+      const int kb0 = sw < S ? (int)(((sw - (int)(kcount % S)) + S) % S) : num_kb;  // owner of stage sw (see loaders)
 #pragma unroll 1
-      for (int kb = sw; kb < num_kb; kb += kSplitWarps) {
+      for (int kb = kb0; kb < num_kb; kb += S) {
         const long long n = kcount + kb;
         const int stage = (int)(n % S), phase = (int)((n / S) & 1);
-        mbar_wait(&raw_full[stage], phase);
+        mbar_wait(&raw_full[stage], phase, 300 + stage);
         uint8_t* a_big = ring + stage * Cfg::kStageBytes;
         if (!(dbg & kDbgNoSplit)) {
 #pragma unroll 8
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         dst = p.dst + m * p.out_c + n_base;                 // NHWC: pixel index m is the row index
         res = p.residual ? p.residual + m * p.out_c + n_base : nullptr;
       }
-      mbar_wait(&acc_full[buf], (use >> 1) & 1);
+      mbar_wait(&acc_full[buf], (use >> 1) & 1, 400 + buf);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
@@ -299,11 +302,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       int m_tile, n_tile, kb_begin, num_kb, split;
       decode(item, m_tile, n_tile, kb_begin, num_kb, split);
       const int buf = use & 1;
-      mbar_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+      mbar_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1, 500 + buf);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_u + (uint32_t)(buf * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full[stage], phase);
+        mbar_wait(&full[stage], phase, 600 + stage + 10 * kb);
         tc_fence_after();
         const uint32_t a_big_u = ring_u + stage * Cfg::kStageBytes, a_small_u = a_big_u + kATileBytes;
         const uint32_t b_big_u = a_big_u + 2 * kATileBytes, b_small_u = b_big_u + Cfg::kBTileBytes;
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       int m_tile, n_tile, kb_begin, num_kb, split;
       decode(item, m_tile, n_tile, kb_begin, num_kb, split);
       const int rb = use & 1;
-      mbar_wait(&ri_empty[rb], ((use >> 1) & 1) ^ 1);
+      mbar_wait(&ri_empty[rb], ((use >> 1) & 1) ^ 1, 700 + rb);
       // lane handles rows 4*lane .. 4*lane+3 (consecutive output pixels): one division, then carry
       long long m = (long long)m_tile * kBM + lane * 4;
       int bb = 0, oy = 0, ox = 0;
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) +
                              ((size_t)n_tile * wk.num_kb_total + kb_begin) * Cfg::kBBytes;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_wait(&empty[stage], phase ^ 1, 800 + stage + 10 * kb);
         if (elect_one()) {
           if (dbg & kDbgNoWeights) {
             mbar_arrive(&full[stage]);

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace dtb200 {
 namespace tc {
@@ -34,7 +35,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug traps (CUDA error after ~2 s) instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   uint32_t addr = smem_u32(bar);
   long long t0 = 0;
   for (uint32_t spin = 0;; ++spin) {
@@ -50,7 +51,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((spin & 0xFFF) == 0xFFF) {
       long long now = clock64();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000LL) __trap();
+      else if (now - t0 > 2000000000LL) {
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)
+          printf("mbar timeout: warp %d tag %d bar@%u parity %u\n", (int)(threadIdx.x >> 5), tag, addr, parity);
+        if (now - t0 > 2400000000LL) __trap();
+      }
     }
   }
 }
