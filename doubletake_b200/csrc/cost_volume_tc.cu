@@ -30,14 +30,21 @@ constexpr int kTProducerWarps = 8;
 constexpr int kTThreads = (kTProducerWarps + 1) * 32;
 constexpr int kTATile = kTRows * 128;            // 16 KB (one of big / small)
 constexpr int kTBTile = kTHidden * 128;          // 16 KB
-constexpr int kTStage = 2 * kTATile + 2 * kTBTile;  // 64 KB
-constexpr int kTStages = 2;
+constexpr int kTAStage = 2 * kTATile;            // A_big | A_small, 32 KB
+constexpr int kTBStage = 2 * kTBTile;            // B_big | B_small, 32 KB
+constexpr int kTStages = 2;                      // A stages (producers <-> MMA)
 
 __host__ __device__ inline int cvtc_nkb1(int K) { return (26 * K + 20 + 31) / 32; }
 __host__ __device__ inline int cvtc_meta_stride(int K) { return ((10 * K + 4 + 3) / 4) * 4 + 4; }
 
+// weight-tile ring depth: as deep as shared memory allows (the tiles are prefetched ahead of the MMAs)
+__host__ __device__ inline int cvtc_bstages(int K) {
+  const int fixed = 1024 + kTStages * kTAStage + kTRows * cvtc_meta_stride(K) * 4 + 4096;
+  int n = (227 * 1024 - fixed) / kTBStage;
+  return n > 4 ? 4 : n;
+}
 size_t cvtc_smem_bytes(int K) {
-  return 1024 + (size_t)kTStages * kTStage + (size_t)kTRows * cvtc_meta_stride(K) * 4 + 4096;
+  return 1024 + (size_t)kTStages * kTAStage + (size_t)cvtc_bstages(K) * kTBStage + (size_t)kTRows * cvtc_meta_stride(K) * 4 + 4096;
 }
 
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -61,8 +68,10 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
   const int nkb1 = cvtc_nkb1(K);
   const int nkb = nkb1 + 4;
   const int MS = cvtc_meta_stride(K);
-  uint8_t* stages = smem;
-  float* meta = reinterpret_cast<float*>(smem + kTStages * kTStage);  // [128][MS]
+  const int SB = cvtc_bstages(K);
+  uint8_t* stages = smem;                                   // A stages
+  uint8_t* b_ring = smem + kTStages * kTAStage;             // weight-tile ring
+  float* meta = reinterpret_cast<float*>(b_ring + (size_t)SB * kTBStage);  // [128][MS]
   uint8_t* tail = reinterpret_cast<uint8_t*>(meta + (size_t)kTRows * MS);
   ViewConst* s_vc = reinterpret_cast<ViewConst*>(tail);                       // [16] x 72 B = 1152
   float* s_partial = reinterpret_cast<float*>(tail + 1280);                   // [2][128]
@@ -72,11 +81,13 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
   float* s_hint = reinterpret_cast<float*>(s_besti + kTPix);                  // [3][16]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 1280 + 4 * (2 * kTRows + kTRows + kTPix + kTPix + 3 * kTPix) + 16);
   bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~(uintptr_t)7);
-  uint64_t* full = bars;            // [2]
-  uint64_t* empty = bars + 2;       // [2]
+  uint64_t* full = bars;            // [2]  A stage filled by the producers
+  uint64_t* empty = bars + 2;       // [2]  A stage consumed (tcgen05.commit)
   uint64_t* d1_full = bars + 4;
   uint64_t* d2_full = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* b_full = bars + 6;      // [4]  weight tile landed (complete_tx)
+  uint64_t* b_empty = bars + 10;    // [4]  weight tile consumed (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
@@ -104,8 +115,12 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
   }
   if (tid == 0) {
     for (int s = 0; s < kTStages; ++s) {
-      mbar_init(&full[s], kTProducerWarps + 1);
+      mbar_init(&full[s], kTProducerWarps);
       mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
     }
     mbar_init(d1_full, 1);
     mbar_init(d2_full, 1);
@@ -258,7 +273,7 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
           }
         }
         mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* a_big = stages + stage * kTStage;
+        uint8_t* a_big = stages + stage * kTAStage;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
@@ -287,7 +302,7 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
         }
         mbar_wait(&empty[stage], phase ^ 1);
         if (mine) {
-          uint8_t* a_big = stages + stage * kTStage;
+          uint8_t* a_big = stages + stage * kTAStage;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint32_t off = (uint32_t)erow * 128u + (uint32_t)((c ^ (erow & 7)) << 4);
@@ -374,24 +389,37 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
     }
   } else {
     // ================================================================================ weight copies + MMA issue
-    // whole warp convergent; single-thread instructions are issued under elect.sync (see tc_common.cuh)
+    // whole warp convergent; single-thread instructions are issued under elect.sync (see tc_common.cuh).
+    // Weight tiles run SB-1 K blocks ahead of the MMAs through their own ring, so their L2 latency is never exposed.
     constexpr uint32_t idesc = umma_idesc_tf32(kTRows, kTHidden);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t stages_u = smem_u32(stages);
+    const uint32_t stages_u = smem_u32(stages), b_ring_u = smem_u32(b_ring);
+    const long long total_u = (long long)num_iters * nkb;
+    auto wtile = [&](long long g) -> const uint8_t* {  // global K-block sequence number -> packed weight tile
+      const int u = (int)(g % nkb);
+      return (u < nkb1) ? reinterpret_cast<const uint8_t*>(w1p) + (size_t)u * kTBStage
+                        : reinterpret_cast<const uint8_t*>(w2p) + (size_t)(u - nkb1) * kTBStage;
+    };
+    auto issue_b = [&](long long g) {  // all lanes; one lane issues
+      const int sb = (int)(g % SB), pb = (int)((g / SB) & 1);
+      mbar_wait(&b_empty[sb], pb ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&b_full[sb], kTBStage);
+        bulk_g2s(b_ring + (size_t)sb * kTBStage, wtile(g), kTBStage, &b_full[sb]);
+      }
+      __syncwarp();
+    };
+    for (long long g = 0; g < SB - 1 && g < total_u; ++g) issue_b(g);
     int stage = 0, phase = 0;
+    long long g = 0;
     for (int iter = 0; iter < num_iters; ++iter) {
-      for (int u = 0; u < nkb; ++u) {
-        const uint32_t a_big_u = stages_u + stage * kTStage, a_small_u = a_big_u + kTATile;
-        const uint32_t b_big_u = a_big_u + 2 * kTATile, b_small_u = b_big_u + kTBTile;
-        const uint8_t* wsrc = (u < nkb1) ? reinterpret_cast<const uint8_t*>(w1p) + (size_t)u * (2 * kTBTile)
-                                         : reinterpret_cast<const uint8_t*>(w2p) + (size_t)(u - nkb1) * (2 * kTBTile);
-        mbar_wait(&empty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&full[stage], 2 * kTBTile);
-          bulk_g2s(stages + stage * kTStage + 2 * kTATile, wsrc, 2 * kTBTile, &full[stage]);
-        }
-        __syncwarp();
+      for (int u = 0; u < nkb; ++u, ++g) {
+        if (g + SB - 1 < total_u) issue_b(g + SB - 1);
+        const int sb = (int)(g % SB), pb = (int)((g / SB) & 1);
+        const uint32_t a_big_u = stages_u + stage * kTAStage, a_small_u = a_big_u + kTATile;
+        const uint32_t b_big_u = b_ring_u + sb * kTBStage, b_small_u = b_big_u + kTBTile;
         mbar_wait(&full[stage], phase);
+        mbar_wait(&b_full[sb], pb);
         tc_fence_after();
         const uint32_t dst = (u < nkb1) ? tmem_u : tmem_u + kTHidden;
         const bool first = (u == 0) || (u == nkb1);
@@ -406,6 +434,7 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
             umma_tf32(dst, da_b, db_b, idesc, true);
           }
           umma_commit(&empty[stage]);
+          umma_commit(&b_empty[sb]);
           if (u == nkb1 - 1) umma_commit(d1_full);
           if (u == nkb - 1) umma_commit(d2_full);
         }
