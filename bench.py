@@ -115,7 +115,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -275,7 +275,9 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.math == "exact" else "f32 via 3xTF32 (tf32 big/small split, fp32 accumulate)",
+            "data": "synthetic",
             "config": {"workload": "cfg2: DoubleTake 640x480 image, 120x160x16 matching feats, 64 planes, 7 src views, "
                                    "rendered-depth hint on, batch 1 per GPU, CVEncoder+DepthDecoderPP (effnetv2-s priors)",
                        "math": args.math, "frames_per_step": frames_per_step,
@@ -295,9 +297,20 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def ncu_traffic():
+    """DRAM bytes per step per kernel family from the committed ncu launch list of this same command
+    (profiles/r01_traffic.json, produced by tools/traffic_from_launches.py); None when absent."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
 def kernel_rooflines(model, dev_sets, cfg, flush, L, reps=5):
     """Live CUDA-event timing of the two kernel families on the launching stream (torch's current stream)."""
     peaks = measured_peaks()
+    traffic = ncu_traffic().get(model.math, {})
     cur, src = dev_sets[0]
     dev = flush.device
     ext, pose = model._relative_poses(cur, src, dev)
@@ -335,7 +348,7 @@ def kernel_rooflines(model, dev_sets, cfg, flush, L, reps=5):
     entries = {
         "cost_volume_mlp_hint": {
             "bound": "tensor", "achieved": round(cv_flops / (cv_ms * 1e-3) / 1e12, 3), "peak": tens_peak, "unit": "TFLOP/s",
-            "frac": round(cv_flops / (cv_ms * 1e-3) / 1e12 / tens_peak, 5), "traffic": None,
+            "frac": round(cv_flops / (cv_ms * 1e-3) / 1e12 / tens_peak, 5), "traffic": traffic.get("cost_volume"),
             "ms_per_launch": round(cv_ms, 4), "launches_per_step": 2,
             "hbm_view": {"bound": "hbm", "achieved": round(cv_bytes / (cv_ms * 1e-3) / 1e9, 2), "peak": peaks["hbm"],
                          "unit": "GB/s", "frac": round(cv_bytes / (cv_ms * 1e-3) / 1e9 / peaks["hbm"], 5),
@@ -343,7 +356,8 @@ def kernel_rooflines(model, dev_sets, cfg, flush, L, reps=5):
             "algorithmic_flops": cv_flops, "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a step)"},
         "conv_stack": {
             "bound": "tensor", "achieved": round(conv_flops / (conv_ms * 1e-3) / 1e12, 3), "peak": tens_peak,
-            "unit": "TFLOP/s", "frac": round(conv_flops / (conv_ms * 1e-3) / 1e12 / tens_peak, 5), "traffic": None,
+            "unit": "TFLOP/s", "frac": round(conv_flops / (conv_ms * 1e-3) / 1e12 / tens_peak, 5),
+            "traffic": traffic.get("conv_stack"),
             "ms_per_launch": round(conv_ms / n_conv, 5), "launches_per_step": n_conv, "ms_all_launches": round(conv_ms, 4),
             "algorithmic_flops": conv_flops, "peak_source": peaks["src"] + " bf16 sustained"},
     }
@@ -456,7 +470,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--math", default="exact", choices=["exact", "tc3x"])
+    ap.add_argument("--math", default="tc3x", choices=["exact", "tc3x"],
+                    help="tc3x: tcgen05 tensor cores with the 3xTF32 split (fp32-class, parity-green); exact: fp32 CUDA cores")
     ap.add_argument("--volume-math", default=None, choices=["exact", "tc3x"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
