@@ -26,31 +26,28 @@ using namespace tc;
 
 constexpr int kBM = 128;                 // pixels per tile (UMMA M)
 constexpr int kBK = 32;                  // fp32 per K block = one 128-byte swizzled row
-constexpr int kLoadWarps = 4;            // cp.async im2col gather; warp w owns K blocks w, w+4, ... of every tile
-constexpr int kSplitWarps = 4;           // smem-only 3xTF32 split + proxy fence, same K-block ownership
+constexpr int kLoadWarps = 4;            // cp.async im2col gather (never fence: they keep many loads in flight)
+constexpr int kSplitWarps = 4;           // smem-only 3xTF32 split + proxy fence
 constexpr int kProducerWarps = kLoadWarps + kSplitWarps;
 constexpr int kEpilogueWarps = 4;
 constexpr int kMmaWarp = kProducerWarps + kEpilogueWarps;      // 12
-constexpr int kAuxWarp = kMmaWarp + 1;                         // 13: weight tiles + row info
-constexpr int kThreads = (kAuxWarp + 1) * 32;                  // 448
+constexpr int kLoaderWarp = kMmaWarp + 1;                      // 13
+constexpr int kThreads = (kLoaderWarp + 1) * 32;               // 448
 constexpr int kATileBytes = kBM * 128;   // 16 KB (one of big / small)
+constexpr int kAStageBytes = 2 * kATileBytes;
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kBTileBytes = BN * 128;
-  static constexpr int kBBytes = 2 * kBTileBytes;                    // B_big | B_small
-  static constexpr int kStageBytes = 2 * kATileBytes + kBBytes;      // A_big | A_small | B_big | B_small
-  static constexpr int kStages = BN <= 64 ? 4 : 3;
-  static constexpr int kTmemCols = 2 * BN;                           // two accumulators
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 2048 /*row info*/ + 512 /*barriers*/;
+  static constexpr int kBStageBytes = 2 * BN * 128;  // B_big | B_small
+  static constexpr int kAStages = BN <= 64 ? 5 : 4;
+  static constexpr int kBStages = 3;
+
+  static constexpr int kTmemCols = 2 * BN;           // two accumulators
+  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 /*align*/ + 1024 /*barriers*/;
 };
 
 __host__ __device__ inline int tc_num_kblocks(int in_c, int ksize) { return (in_c * ksize * ksize + kBK - 1) / kBK; }
 __host__ __device__ inline int tc_bn(int out_c) { return (out_c % 128 == 0) ? 128 : 64; }
-
-// development switches (dtb200_debug_set): knock out one pipeline component to locate bottlenecks; 0 in production
-__device__ int g_conv_debug = 0;
-constexpr int kDbgNoLoads = 1, kDbgNoSplit = 2, kDbgNoMma = 4, kDbgNoEpilogueIO = 8, kDbgNoWeights = 16;
 
 struct TcWork {  // persistent tile scheduler: item -> (m tile, n tile, K split)
   int m_tiles, n_tiles, splits, kb_per_split, num_kb_total;
@@ -58,41 +55,34 @@ struct TcWork {  // persistent tile scheduler: item -> (m tile, n tile, K split)
 };
 
 // Persistent warp-specialised implicit-GEMM conv.  One CTA per SM loops over work items (static stride).
-//   warps 0-3   A loaders (warp w owns stage w; warps >= kStages idle): raw fp32 im2col rows by cp.async (zero-fill = padding) into the swizzled A_big tile; completion is
-//               signalled by the hardware (cp.async.mbarrier.arrive.noinc), the warp never fences and never waits on data
-//   warps 4-7   A splitters: A_big (raw) -> tf32-truncated big in place + small = x - big; fence.proxy.async; arrive
+//   warps 0-7   A producers: im2col gather -> 3xTF32 split -> SWIZZLE_128B tiles (4-deep ring)
 //   warps 8-11  epilogue: TMEM -> bias/residual/activation -> NHWC store (or split-K partials); double-buffered accumulator
-//   warp 12     MMA issuer (convergent warp, elect.sync): 12 tcgen05.mma per K block, tcgen05.commit frees the stage
-//   warp 13     weight tiles by cp.async.bulk into the same stage/barrier as A, plus next tile's row info (pixel index and
-//               zero-padding tap mask of the 128 rows) so the loaders start every tile without a prologue
-// Loader / splitter warp w owns the K blocks whose global sequence number n has n % kStages == w (always stage w), so
-// kStages K blocks are in flight per role and every waiter observes each phase of its barriers in order.
+//   warp 12     MMA issuer (one lane): 12 tcgen05.mma per K block, tcgen05.commit frees the A and B stages
+//   warp 13     weight-tile loader (one lane): cp.async.bulk of the pre-swizzled [B_big|B_small] tile, running ahead
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_params p, int in_c_total, long long m_total,
                                                               TcWork wk, float* __restrict__ partial) {
   using Cfg = TcCfg<BN>;
-  constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* ring = smem;
-  int2* rowinfo = reinterpret_cast<int2*>(ring + S * Cfg::kStageBytes);       // [2][128] {centre pixel index, tap mask}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rowinfo) + 2048);
-  uint64_t* raw_full = bars;            // [S] loaders  -> splitters (cp.async completion, 32 arrivals)
-  uint64_t* full = raw_full + S;        // [S] splitter + weight copy -> MMA
-  uint64_t* empty = full + S;           // [S] MMA (tcgen05.commit) -> loaders, weight loader
-  uint64_t* acc_full = empty + S;       // [2]
-  uint64_t* acc_empty = acc_full + 2;   // [2]
-  uint64_t* ri_full = acc_empty + 2;    // [2]
-  uint64_t* ri_empty = ri_full + 2;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ri_empty + 2);
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + Cfg::kAStages * kAStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + Cfg::kBStages * Cfg::kBStageBytes);
+  uint64_t* raw_full = bars;                      // loaders -> splitters (cp.async completion)
+  uint64_t* a_full = raw_full + Cfg::kAStages;    // splitters -> MMA
+  uint64_t* a_empty = a_full + Cfg::kAStages;     // MMA -> loaders
+  uint64_t* b_full = a_empty + Cfg::kAStages;
+  uint64_t* b_empty = b_full + Cfg::kBStages;
+  uint64_t* acc_full = b_empty + Cfg::kBStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(&raw_full[s], 32), mbar_init(&full[s], 2), mbar_init(&empty[s], 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&acc_full[s], 1), mbar_init(&acc_empty[s], kEpilogueWarps);
-      mbar_init(&ri_full[s], 1), mbar_init(&ri_empty[s], kLoadWarps);
-    }
+    for (int s = 0; s < Cfg::kAStages; ++s)
+      mbar_init(&raw_full[s], kLoadWarps * 32), mbar_init(&a_full[s], kSplitWarps), mbar_init(&a_empty[s], 1);
+    for (int s = 0; s < Cfg::kBStages; ++s) mbar_init(&b_full[s], 1), mbar_init(&b_empty[s], 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&acc_full[s], 1), mbar_init(&acc_empty[s], kEpilogueWarps);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -101,7 +91,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int hw = p.out_h * p.out_w;
-  const int dbg = g_conv_debug;
 
   auto decode = [&](long long item, int& m_tile, int& n_tile, int& kb_begin, int& num_kb, int& split) {
     split = (int)(item % wk.splits);
@@ -113,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
   };
 
   if (warp < kLoadWarps) {
-    // ============================================================ A loaders
+    // ============================================================ A loaders: raw fp32 im2col rows by cp.async
     SrcView sv[DTB200_CONV_MAX_SRC];
     int grp_end[DTB200_CONV_MAX_SRC];
     int acc_g = 0;
@@ -131,29 +120,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
     const int groups_per_tap = in_c_total / 8;
     const int taps = p.ksize * p.ksize;
     const int pad = p.ksize / 2;
-    const int q = lane & 7;          // 16-byte chunk of the 128-byte row
-    const int rg = lane >> 3;        // rows rg + 4*it, it = 0..31
-    long long kcount = 0;            // K blocks issued so far (all tiles): stage / phase of the next one
-    int use = 0;
-    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
+    const int q = tid & 7;          // 16-byte chunk of the 128-byte row this thread fills
+    const int prow = tid >> 3;      // rows prow + 16*it, it = 0..7
+    int stage = 0, phase = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
       int m_tile, n_tile, kb_begin, num_kb, split;
       decode(item, m_tile, n_tile, kb_begin, num_kb, split);
-      const int rb = use & 1;
-      mbar_wait(&ri_full[rb], (use >> 1) & 1, 100 + rb);
-      const int2* ri = rowinfo + rb * kBM;
-      // Ownership by GLOBAL sequence number: warp w owns the K blocks with n % S == w, i.e. always stage w, so it observes
-      // every phase of its stage's barriers in order (a parity wait must never skip a phase).  Warps >= S idle.
-      const int kb0 = warp < S ? (int)(((warp - (int)(kcount % S)) + S) % S) : num_kb;
+      // per-row state for this tile: centre-tap pixel index and tap validity mask (zero padding)
+      int pix_center[8];
+      uint32_t tap_mask[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const long long m = (long long)m_tile * kBM + prow + it * 16;
+        uint32_t mask = 0;
+        int pc = 0;
+        if (m < m_total) {
+          const int bb = (int)(m / hw);
+          const int r = (int)(m - (long long)bb * hw);
+          const int oy = r / p.out_w, ox = r - oy * p.out_w;
+          const int cy = oy * p.stride, cx = ox * p.stride;
+          for (int t = 0; t < taps; ++t) {
+            int iy = cy + t / p.ksize - pad, ix = cx + t % p.ksize - pad;
+            if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) mask |= 1u << t;
+          }
+          pc = (bb * p.in_h + cy) * p.in_w + cx;
+        }
+        pix_center[it] = pc;
+        tap_mask[it] = mask;
+      }
+      // group cursor of this thread's chunk: (tap, group-in-tap), advanced by 4 groups per K block
       int g_tap, g_r;
       {
-        const int g = (kb_begin + kb0) * 4 + (q >> 1);
+        const int g = kb_begin * 4 + (q >> 1);
         g_tap = g / groups_per_tap;
         g_r = g - g_tap * groups_per_tap;
       }
 #pragma unroll 1
-      for (int kb = kb0; kb < num_kb; kb += S) {
-        const long long n = kcount + kb;
-        const int stage = (int)(n % S), phase = (int)((n / S) & 1);
+      for (int kb = 0; kb < num_kb; ++kb) {
         const bool g_ok = g_tap < taps;
         const int tap = g_ok ? g_tap : 0;
         const int src_i = g_r < grp_end[0] ? 0 : (g_r < grp_end[1] ? 1 : 2);
@@ -163,28 +166,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         SrcView my = sv[0];
         if (src_i == 1) my = sv[1];
         if (src_i == 2) my = sv[2];
-        mbar_wait(&empty[stage], phase ^ 1, 200 + stage + 10 * (int)(n & 7));
-        uint8_t* a_big = ring + stage * Cfg::kStageBytes;
-        if (dbg & kDbgNoLoads) {
-        } else if (my.resample == DTB200_RESAMPLE_NONE) {
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        uint8_t* a_big = a_ring + stage * kAStageBytes;
+        if (my.resample == DTB200_RESAMPLE_NONE) {
           const int dpix = (ky - pad) * p.in_w + (kx - pad);
           const float* bp = my.ptr + c0;
-#pragma unroll 8
-          for (int it = 0; it < 32; ++it) {
-            const int row = rg + it * 4;
-            const int2 info = ri[row];
-            const bool ok = g_ok && ((info.y >> tap) & 1);
-            const long long off = ok ? (long long)(info.x + dpix) * my.c : 0;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = prow + it * 16;
+            const bool ok = g_ok && ((tap_mask[it] >> tap) & 1u);
+            const long long off = ok ? (long long)(pix_center[it] + dpix) * my.c : 0;
             cp_async16(a_big + (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4), bp + off, ok ? 16u : 0u);
           }
         } else {
           // generic path: x2 up-sampling on load (the TC plans normally materialise up-sampled maps instead)
-#pragma unroll 1
-          for (int it = 0; it < 32; ++it) {
-            const int row = rg + it * 4;
-            const int2 info = ri[row];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = prow + it * 16;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g_ok && info.y != 0) {
+            if (g_ok && tap_mask[it] != 0u) {
               const long long m = (long long)m_tile * kBM + row;
               const int bb = (int)(m / hw);
               const int r = (int)(m - (long long)bb * hw);
@@ -195,46 +195,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
           }
           __threadfence_block();
         }
-        cp_async_mbar_arrive(&raw_full[stage]);  // fires when this lane's copies have landed; the warp moves on
-        g_r += 4 * S;
+        cp_async_mbar_arrive(&raw_full[stage]);  // fires when this thread's copies have landed; the thread moves on
+        if (++stage == Cfg::kAStages) stage = 0, phase ^= 1;
+        g_r += 4;
         while (g_r >= groups_per_tap) g_r -= groups_per_tap, ++g_tap;
       }
-      kcount += num_kb;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ri_empty[rb]);
     }
   } else if (warp < kProducerWarps) {
-    // ============================================================ A splitters
-    const int sw = warp - kLoadWarps;
-    const int q = lane & 7, rg = lane >> 3;
-    long long kcount = 0;
+    // ============================================================ A splitters: raw -> (big, small), shared memory only
+    const int st = tid - kLoadWarps * 32;
+    const int q = st & 7, prow = st >> 3;
+    uint32_t soff[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = prow + it * 16;
+      soff[it] = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
+    }
+    int stage = 0, phase = 0;
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
       int m_tile, n_tile, kb_begin, num_kb, split;
       decode(item, m_tile, n_tile, kb_begin, num_kb, split);
-      const int kb0 = sw < S ? (int)(((sw - (int)(kcount % S)) + S) % S) : num_kb;  // owner of stage sw (see loaders)
 #pragma unroll 1
-      for (int kb = kb0; kb < num_kb; kb += S) {
-        const long long n = kcount + kb;
-        const int stage = (int)(n % S), phase = (int)((n / S) & 1);
-        mbar_wait(&raw_full[stage], phase, 300 + stage);
-        uint8_t* a_big = ring + stage * Cfg::kStageBytes;
-        if (!(dbg & kDbgNoSplit)) {
-#pragma unroll 8
-          for (int it = 0; it < 32; ++it) {
-            const int row = rg + it * 4;
-            const uint32_t off = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
-            const float4 v = *reinterpret_cast<const float4*>(a_big + off);
-            float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
-            float4 small = make_float4(v.x - big.x, v.y - big.y, v.z - big.z, v.w - big.w);
-            *reinterpret_cast<float4*>(a_big + off) = big;
-            *reinterpret_cast<float4*>(a_big + kATileBytes + off) = small;
-          }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&raw_full[stage], phase);
+        uint8_t* a_big = a_ring + stage * kAStageBytes;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float4 v = *reinterpret_cast<const float4*>(a_big + soff[it]);
+          float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
+          float4 small = make_float4(v.x - big.x, v.y - big.y, v.z - big.z, v.w - big.w);
+          *reinterpret_cast<float4*>(a_big + soff[it]) = big;
+          *reinterpret_cast<float4*>(a_big + kATileBytes + soff[it]) = small;
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full[stage]);
+        if (lane == 0) mbar_arrive(&a_full[stage]);
+        if (++stage == Cfg::kAStages) stage = 0, phase ^= 1;
       }
-      kcount += num_kb;
     }
   } else if (warp < kMmaWarp) {
     // ============================================================ epilogue warps
@@ -248,6 +245,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       const long long m = (long long)m_tile * kBM + row;
       const bool live = m < m_total;
       const int n_base = n_tile * BN;
+      mbar_wait(&acc_full[buf], (use >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(ew * 32) << 16);
       float* dst = nullptr;
       const float* res = nullptr;
       if (partial) {
@@ -256,14 +256,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         dst = p.dst + m * p.out_c + n_base;                 // NHWC: pixel index m is the row index
         res = p.residual ? p.residual + m * p.out_c + n_base : nullptr;
       }
-      mbar_wait(&acc_full[buf], (use >> 1) & 1, 400 + buf);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += 32) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)cc, v);
-        if (!live || (dbg & kDbgNoEpilogueIO)) continue;
+        if (!live) continue;
         if (partial) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -296,24 +293,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
     // ============================================================ MMA issuer (whole warp convergent; elect.sync issues)
     constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t ring_u = smem_u32(ring);
-    int stage = 0, phase = 0, use = 0;
+    const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
+    int sa = 0, pa = 0, sb = 0, pb = 0, use = 0;
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
       int m_tile, n_tile, kb_begin, num_kb, split;
       decode(item, m_tile, n_tile, kb_begin, num_kb, split);
       const int buf = use & 1;
-      mbar_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1, 500 + buf);  // epilogue has drained this accumulator
+      mbar_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_u + (uint32_t)(buf * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full[stage], phase, 600 + stage + 10 * kb);
+        mbar_wait(&a_full[sa], pa);
+        mbar_wait(&b_full[sb], pb);
         tc_fence_after();
-        const uint32_t a_big_u = ring_u + stage * Cfg::kStageBytes, a_small_u = a_big_u + kATileBytes;
-        const uint32_t b_big_u = a_big_u + 2 * kATileBytes, b_small_u = b_big_u + Cfg::kBTileBytes;
+        const uint32_t a_big_u = a_ring_u + sa * kAStageBytes, a_small_u = a_big_u + kATileBytes;
+        const uint32_t b_big_u = b_ring_u + sb * Cfg::kBStageBytes, b_small_u = b_big_u + BN * 128;
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            if (dbg & kDbgNoMma) break;
             const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes along K inside the swizzled row
             const uint64_t da_b = umma_desc_k128(a_big_u + ko), da_s = umma_desc_k128(a_small_u + ko);
             const uint64_t db_b = umma_desc_k128(b_big_u + ko), db_s = umma_desc_k128(b_small_u + ko);
@@ -321,76 +318,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
             umma_tf32(tmem_d, da_b, db_s, idesc, true);
             umma_tf32(tmem_d, da_b, db_b, idesc, true);
           }
-          umma_commit(&empty[stage]);
+          umma_commit(&a_empty[sa]);
+          umma_commit(&b_empty[sb]);
         }
         __syncwarp();
-        if (++stage == S) stage = 0, phase ^= 1;
+        if (++sa == Cfg::kAStages) sa = 0, pa ^= 1;
+        if (++sb == Cfg::kBStages) sb = 0, pb ^= 1;
       }
       if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
     }
   } else {
-    // ============================================================ aux warp: row info one tile ahead + weight tiles
-    const int taps = p.ksize * p.ksize;
-    const int pad = p.ksize / 2;
-    auto write_rowinfo = [&](long long item, int use) {
-      int m_tile, n_tile, kb_begin, num_kb, split;
-      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
-      const int rb = use & 1;
-      mbar_wait(&ri_empty[rb], ((use >> 1) & 1) ^ 1, 700 + rb);
-      // lane handles rows 4*lane .. 4*lane+3 (consecutive output pixels): one division, then carry
-      long long m = (long long)m_tile * kBM + lane * 4;
-      int bb = 0, oy = 0, ox = 0;
-      if (m < m_total) {
-        bb = (int)(m / hw);
-        const int r = (int)(m - (long long)bb * hw);
-        oy = r / p.out_w;
-        ox = r - oy * p.out_w;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j, ++m) {
-        int2 info = make_int2(0, 0);
-        if (m < m_total) {
-          const int cy = oy * p.stride, cx = ox * p.stride;
-          int mask = 0, t = 0;
-          for (int ky = 0; ky < p.ksize; ++ky)
-            for (int kx = 0; kx < p.ksize; ++kx, ++t) {
-              const int iy = cy + ky - pad, ix = cx + kx - pad;
-              if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) mask |= 1 << t;
-            }
-          info = make_int2((bb * p.in_h + cy) * p.in_w + cx, mask);
-          if (++ox == p.out_w) {
-            ox = 0;
-            if (++oy == p.out_h) oy = 0, ++bb;
-          }
-        }
-        rowinfo[rb * kBM + lane * 4 + j] = info;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ri_full[rb]);
-    };
-    (void)taps;
-    int stage = 0, phase = 0, use = 0;
-    if ((long long)blockIdx.x < wk.total) write_rowinfo(blockIdx.x, 0);
-    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
-      if (item + gridDim.x < wk.total) write_rowinfo(item + gridDim.x, use + 1);
+    // ============================================================ weight-tile loader (whole warp convergent)
+    int sb = 0, pb = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
       int m_tile, n_tile, kb_begin, num_kb, split;
       decode(item, m_tile, n_tile, kb_begin, num_kb, split);
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) +
-                             ((size_t)n_tile * wk.num_kb_total + kb_begin) * Cfg::kBBytes;
+                             ((size_t)n_tile * wk.num_kb_total + kb_begin) * Cfg::kBStageBytes;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1, 800 + stage + 10 * kb);
+        mbar_wait(&b_empty[sb], pb ^ 1);
         if (elect_one()) {
-          if (dbg & kDbgNoWeights) {
-            mbar_arrive(&full[stage]);
-          } else {
-            mbar_arrive_expect_tx(&full[stage], Cfg::kBBytes);
-            bulk_g2s(ring + stage * Cfg::kStageBytes + 2 * kATileBytes, wbase + (size_t)kb * Cfg::kBBytes, Cfg::kBBytes,
-                     &full[stage]);
-          }
+          mbar_arrive_expect_tx(&b_full[sb], Cfg::kBStageBytes);
+          bulk_g2s(b_ring + sb * Cfg::kBStageBytes, wbase + (size_t)kb * Cfg::kBStageBytes, Cfg::kBStageBytes, &b_full[sb]);
         }
         __syncwarp();
-        if (++stage == S) stage = 0, phase ^= 1;
+        if (++sb == Cfg::kBStages) sb = 0, pb ^= 1;
       }
     }
   }
@@ -429,10 +382,7 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ oihw, float* __r
 
 int launch_conv_simt(const dtb200_conv_params& p, int in_c_total, cudaStream_t stream);
 
-int conv_tc_debug_set(int flags) {
-  cudaError_t e = cudaMemcpyToSymbol(g_conv_debug, &flags, sizeof(int));
-  return e == cudaSuccess ? DTB200_OK : fail(DTB200_ERR_CUDA, "debug_set: %s", cudaGetErrorString(e));
-}
+int conv_tc_debug_set(int) { return DTB200_OK; }  // development hook (knock-out switches live on the experiment branch)
 
 uint64_t packed_floats_tc(int out_c, int in_c, int ksize) {
   if (out_c % 64 != 0) return (uint64_t)out_c * in_c * ksize * ksize;  // heads stay on the SIMT layout
