@@ -33,7 +33,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcuda"]
+    extra = os.environ.get("DTB200_NVCC_EXTRA", "").split()  # development switches, e.g. -DDTB200_RAW_BIG
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcuda"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

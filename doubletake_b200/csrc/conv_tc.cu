@@ -31,19 +31,18 @@ constexpr int kSplitWarps = 4;           // smem-only 3xTF32 split + proxy fence
 constexpr int kProducerWarps = kLoadWarps + kSplitWarps;
 constexpr int kEpilogueWarps = 4;
 constexpr int kMmaWarp = kProducerWarps + kEpilogueWarps;      // 12
-constexpr int kLoaderWarp = kMmaWarp + 1;                      // 13
-constexpr int kThreads = (kLoaderWarp + 1) * 32;               // 448
+constexpr int kAuxWarp = kMmaWarp + 1;                         // 13: weight tiles + row info
+constexpr int kThreads = (kAuxWarp + 1) * 32;                  // 448
 constexpr int kATileBytes = kBM * 128;   // 16 KB (one of big / small)
-constexpr int kAStageBytes = 2 * kATileBytes;
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kBStageBytes = 2 * BN * 128;  // B_big | B_small
-  static constexpr int kAStages = BN <= 64 ? 5 : 4;
-  static constexpr int kBStages = 3;
-
-  static constexpr int kTmemCols = 2 * BN;           // two accumulators
-  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 /*align*/ + 1024 /*barriers*/;
+  static constexpr int kBTileBytes = BN * 128;
+  static constexpr int kBBytes = 2 * kBTileBytes;                    // B_big | B_small
+  static constexpr int kStageBytes = 2 * kATileBytes + kBBytes;      // A_big | A_small | B_big | B_small
+  static constexpr int kStages = BN <= 64 ? 4 : 3;
+  static constexpr int kTmemCols = 2 * BN;                           // two accumulators
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 2048 /*row info*/ + 512 /*barriers*/;
 };
 
 __host__ __device__ inline int tc_num_kblocks(int in_c, int ksize) { return (in_c * ksize * ksize + kBK - 1) / kBK; }
@@ -58,31 +57,35 @@ struct TcWork {  // persistent tile scheduler: item -> (m tile, n tile, K split)
 //   warps 0-7   A producers: im2col gather -> 3xTF32 split -> SWIZZLE_128B tiles (4-deep ring)
 //   warps 8-11  epilogue: TMEM -> bias/residual/activation -> NHWC store (or split-K partials); double-buffered accumulator
 //   warp 12     MMA issuer (one lane): 12 tcgen05.mma per K block, tcgen05.commit frees the A and B stages
-//   warp 13     weight-tile loader (one lane): cp.async.bulk of the pre-swizzled [B_big|B_small] tile, running ahead
+//   warp 13     aux: weight tiles by cp.async.bulk into the same stage/barrier as A (one MMA-side wait per K block), and
+//               the NEXT tile's row info (pixel index + zero-padding tap mask per row) so loaders start tiles without a prologue
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_params p, int in_c_total, long long m_total,
                                                               TcWork wk, float* __restrict__ partial) {
   using Cfg = TcCfg<BN>;
+  constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_ring = smem;
-  uint8_t* b_ring = smem + Cfg::kAStages * kAStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + Cfg::kBStages * Cfg::kBStageBytes);
-  uint64_t* raw_full = bars;                      // loaders -> splitters (cp.async completion)
-  uint64_t* a_full = raw_full + Cfg::kAStages;    // splitters -> MMA
-  uint64_t* a_empty = a_full + Cfg::kAStages;     // MMA -> loaders
-  uint64_t* b_full = a_empty + Cfg::kAStages;
-  uint64_t* b_empty = b_full + Cfg::kBStages;
-  uint64_t* acc_full = b_empty + Cfg::kBStages;   // [2]
-  uint64_t* acc_empty = acc_full + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* ring = smem;                                                       // S x [A_big|A_small|B_big|B_small]
+  int2* rowinfo = reinterpret_cast<int2*>(ring + S * Cfg::kStageBytes);       // [2][128] {centre pixel index, tap mask}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rowinfo) + 2048);
+  uint64_t* raw_full = bars;            // [S] loaders -> splitters (cp.async completion, 128 arrivals)
+  uint64_t* full = raw_full + S;        // [S] splitters (4) + weight copy (1 + tx) -> MMA: ONE wait per K block
+  uint64_t* empty = full + S;           // [S] MMA (tcgen05.commit) -> loaders, weight loader
+  uint64_t* acc_full = empty + S;       // [2]
+  uint64_t* acc_empty = acc_full + 2;   // [2]
+  uint64_t* ri_full = acc_empty + 2;    // [2] row info of the next tile written
+  uint64_t* ri_empty = ri_full + 2;     // [2] loaders done with it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ri_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < Cfg::kAStages; ++s)
-      mbar_init(&raw_full[s], kLoadWarps * 32), mbar_init(&a_full[s], kSplitWarps), mbar_init(&a_empty[s], 1);
-    for (int s = 0; s < Cfg::kBStages; ++s) mbar_init(&b_full[s], 1), mbar_init(&b_empty[s], 1);
-    for (int s = 0; s < 2; ++s) mbar_init(&acc_full[s], 1), mbar_init(&acc_empty[s], kEpilogueWarps);
+    for (int s = 0; s < S; ++s)
+      mbar_init(&raw_full[s], kLoadWarps * 32), mbar_init(&full[s], kSplitWarps + 1), mbar_init(&empty[s], 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1), mbar_init(&acc_empty[s], kEpilogueWarps);
+      mbar_init(&ri_full[s], 1), mbar_init(&ri_empty[s], kLoadWarps);
+    }
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -122,32 +125,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
     const int pad = p.ksize / 2;
     const int q = tid & 7;          // 16-byte chunk of the 128-byte row this thread fills
     const int prow = tid >> 3;      // rows prow + 16*it, it = 0..7
-    int stage = 0, phase = 0;
-    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
+    uint32_t soff[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = prow + it * 16;
+      soff[it] = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
+    }
+    int stage = 0, phase = 0, use = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
       int m_tile, n_tile, kb_begin, num_kb, split;
       decode(item, m_tile, n_tile, kb_begin, num_kb, split);
-      // per-row state for this tile: centre-tap pixel index and tap validity mask (zero padding)
-      int pix_center[8];
-      uint32_t tap_mask[8];
+      const int rb = use & 1;
+      mbar_wait(&ri_full[rb], (use >> 1) & 1);   // row info of this tile (written one tile ahead by the aux warp)
+      int2 info[8];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const long long m = (long long)m_tile * kBM + prow + it * 16;
-        uint32_t mask = 0;
-        int pc = 0;
-        if (m < m_total) {
-          const int bb = (int)(m / hw);
-          const int r = (int)(m - (long long)bb * hw);
-          const int oy = r / p.out_w, ox = r - oy * p.out_w;
-          const int cy = oy * p.stride, cx = ox * p.stride;
-          for (int t = 0; t < taps; ++t) {
-            int iy = cy + t / p.ksize - pad, ix = cx + t % p.ksize - pad;
-            if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) mask |= 1u << t;
-          }
-          pc = (bb * p.in_h + cy) * p.in_w + cx;
-        }
-        pix_center[it] = pc;
-        tap_mask[it] = mask;
-      }
+      for (int it = 0; it < 8; ++it) info[it] = rowinfo[rb * kBM + prow + it * 16];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ri_empty[rb]);  // copied to registers: the buffer can be rewritten
       // group cursor of this thread's chunk: (tap, group-in-tap), advanced by 4 groups per K block
       int g_tap, g_r;
       {
@@ -166,43 +160,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         SrcView my = sv[0];
         if (src_i == 1) my = sv[1];
         if (src_i == 2) my = sv[2];
-        mbar_wait(&a_empty[stage], phase ^ 1);
-        uint8_t* a_big = a_ring + stage * kAStageBytes;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* a_big = ring + stage * Cfg::kStageBytes;
         if (my.resample == DTB200_RESAMPLE_NONE) {
           const int dpix = (ky - pad) * p.in_w + (kx - pad);
           const float* bp = my.ptr + c0;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            const int row = prow + it * 16;
-            const bool ok = g_ok && ((tap_mask[it] >> tap) & 1u);
-            const long long off = ok ? (long long)(pix_center[it] + dpix) * my.c : 0;
-            cp_async16(a_big + (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4), bp + off, ok ? 16u : 0u);
+            const bool ok = g_ok && ((info[it].y >> tap) & 1);
+            const long long off = ok ? (long long)(info[it].x + dpix) * my.c : 0;
+            cp_async16(a_big + soff[it], bp + off, ok ? 16u : 0u);
           }
         } else {
           // generic path: x2 up-sampling on load (the TC plans normally materialise up-sampled maps instead)
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            const int row = prow + it * 16;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g_ok && tap_mask[it] != 0u) {
-              const long long m = (long long)m_tile * kBM + row;
+            if (g_ok && info[it].y != 0) {
+              const long long m = (long long)m_tile * kBM + prow + it * 16;
               const int bb = (int)(m / hw);
               const int r = (int)(m - (long long)bb * hw);
               const int oy = r / p.out_w, ox = r - oy * p.out_w;
               v = load_input4(my, bb, oy * p.stride + ky - pad, ox * p.stride + kx - pad, p.in_h, p.in_w, c0);
             }
-            *reinterpret_cast<float4*>(a_big + (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4)) = v;
+            *reinterpret_cast<float4*>(a_big + soff[it]) = v;
           }
           __threadfence_block();
         }
         cp_async_mbar_arrive(&raw_full[stage]);  // fires when this thread's copies have landed; the thread moves on
-        if (++stage == Cfg::kAStages) stage = 0, phase ^= 1;
+        if (++stage == S) stage = 0, phase ^= 1;
         g_r += 4;
         while (g_r >= groups_per_tap) g_r -= groups_per_tap, ++g_tap;
       }
     }
   } else if (warp < kProducerWarps) {
-    // ============================================================ A splitters: raw -> (big, small), shared memory only
+    // ============================================================ A splitters: small = x - tf32(x), shared memory only
+    // The raw fp32 tile stays in place as the "big" operand: kind::tf32 ignores the low 13 mantissa bits of its
+    // operands (verified on B200: every parity test passes bit-for-bit as with an explicit mask), so big = trunc(x)
+    // needs no store.  Define DTB200_MASK_BIG to write the masked value anyway.
     const int st = tid - kLoadWarps * 32;
     const int q = st & 7, prow = st >> 3;
     uint32_t soff[8];
@@ -218,19 +213,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
 #pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&raw_full[stage], phase);
-        uint8_t* a_big = a_ring + stage * kAStageBytes;
+        uint8_t* a_big = ring + stage * Cfg::kStageBytes;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const float4 v = *reinterpret_cast<const float4*>(a_big + soff[it]);
           float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
           float4 small = make_float4(v.x - big.x, v.y - big.y, v.z - big.z, v.w - big.w);
+#ifdef DTB200_MASK_BIG
           *reinterpret_cast<float4*>(a_big + soff[it]) = big;
+#endif
           *reinterpret_cast<float4*>(a_big + kATileBytes + soff[it]) = small;
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[stage]);
-        if (++stage == Cfg::kAStages) stage = 0, phase ^= 1;
+        if (lane == 0) mbar_arrive(&full[stage]);
+        if (++stage == S) stage = 0, phase ^= 1;
       }
     }
   } else if (warp < kMmaWarp) {
@@ -245,9 +242,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       const long long m = (long long)m_tile * kBM + row;
       const bool live = m < m_total;
       const int n_base = n_tile * BN;
-      mbar_wait(&acc_full[buf], (use >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(ew * 32) << 16);
       float* dst = nullptr;
       const float* res = nullptr;
       if (partial) {
@@ -256,6 +250,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         dst = p.dst + m * p.out_c + n_base;                 // NHWC: pixel index m is the row index
         res = p.residual ? p.residual + m * p.out_c + n_base : nullptr;
       }
+      mbar_wait(&acc_full[buf], (use >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += 32) {
         float v[32];
@@ -293,8 +290,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
     // ============================================================ MMA issuer (whole warp convergent; elect.sync issues)
     constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
-    int sa = 0, pa = 0, sb = 0, pb = 0, use = 0;
+    const uint32_t ring_u = smem_u32(ring);
+    int stage = 0, phase = 0, use = 0;
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
       int m_tile, n_tile, kb_begin, num_kb, split;
       decode(item, m_tile, n_tile, kb_begin, num_kb, split);
@@ -303,11 +300,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       tc_fence_after();
       const uint32_t tmem_d = tmem_u + (uint32_t)(buf * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&a_full[sa], pa);
-        mbar_wait(&b_full[sb], pb);
+        mbar_wait(&full[stage], phase);                  // A (split) and B (weight tile) of this K block are in place
         tc_fence_after();
-        const uint32_t a_big_u = a_ring_u + sa * kAStageBytes, a_small_u = a_big_u + kATileBytes;
-        const uint32_t b_big_u = b_ring_u + sb * Cfg::kBStageBytes, b_small_u = b_big_u + BN * 128;
+        const uint32_t a_big_u = ring_u + stage * Cfg::kStageBytes, a_small_u = a_big_u + kATileBytes;
+        const uint32_t b_big_u = a_big_u + 2 * kATileBytes, b_small_u = b_big_u + Cfg::kBTileBytes;
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
@@ -318,32 +314,70 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
             umma_tf32(tmem_d, da_b, db_s, idesc, true);
             umma_tf32(tmem_d, da_b, db_b, idesc, true);
           }
-          umma_commit(&a_empty[sa]);
-          umma_commit(&b_empty[sb]);
+          umma_commit(&empty[stage]);
         }
         __syncwarp();
-        if (++sa == Cfg::kAStages) sa = 0, pa ^= 1;
-        if (++sb == Cfg::kBStages) sb = 0, pb ^= 1;
+        if (++stage == S) stage = 0, phase ^= 1;
       }
       if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
     }
   } else {
-    // ============================================================ weight-tile loader (whole warp convergent)
-    int sb = 0, pb = 0;
-    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
+    // ============================================================ aux warp: next tile's row info + weight tiles
+    const int pad = p.ksize / 2;
+    auto write_rowinfo = [&](long long item, int use) {
+      int m_tile, n_tile, kb_begin, num_kb, split;
+      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
+      const int rb = use & 1;
+      mbar_wait(&ri_empty[rb], ((use >> 1) & 1) ^ 1);
+      // lane handles rows 4*lane .. 4*lane+3 (consecutive output pixels): one division, then carry
+      long long m = (long long)m_tile * kBM + lane * 4;
+      int bb = 0, oy = 0, ox = 0;
+      if (m < m_total) {
+        bb = (int)(m / hw);
+        const int r = (int)(m - (long long)bb * hw);
+        oy = r / p.out_w;
+        ox = r - oy * p.out_w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j, ++m) {
+        int2 info = make_int2(0, 0);
+        if (m < m_total) {
+          const int cy = oy * p.stride, cx = ox * p.stride;
+          int mask = 0, t = 0;
+          for (int ky = 0; ky < p.ksize; ++ky)
+            for (int kx = 0; kx < p.ksize; ++kx, ++t) {
+              const int iy = cy + ky - pad, ix = cx + kx - pad;
+              if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) mask |= 1 << t;
+            }
+          info = make_int2((bb * p.in_h + cy) * p.in_w + cx, mask);
+          if (++ox == p.out_w) {
+            ox = 0;
+            if (++oy == p.out_h) oy = 0, ++bb;
+          }
+        }
+        rowinfo[rb * kBM + lane * 4 + j] = info;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ri_full[rb]);
+    };
+    int stage = 0, phase = 0, use = 0;
+    if ((long long)blockIdx.x < wk.total) write_rowinfo(blockIdx.x, 0);
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
+      if (item + gridDim.x < wk.total) write_rowinfo(item + gridDim.x, use + 1);
       int m_tile, n_tile, kb_begin, num_kb, split;
       decode(item, m_tile, n_tile, kb_begin, num_kb, split);
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) +
-                             ((size_t)n_tile * wk.num_kb_total + kb_begin) * Cfg::kBStageBytes;
+                             ((size_t)n_tile * wk.num_kb_total + kb_begin) * Cfg::kBBytes;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&b_empty[sb], pb ^ 1);
+        mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&b_full[sb], Cfg::kBStageBytes);
-          bulk_g2s(b_ring + sb * Cfg::kBStageBytes, wbase + (size_t)kb * Cfg::kBStageBytes, Cfg::kBStageBytes, &b_full[sb]);
+          mbar_arrive_expect_tx(&full[stage], Cfg::kBBytes);
+          bulk_g2s(ring + stage * Cfg::kStageBytes + 2 * kATileBytes, wbase + (size_t)kb * Cfg::kBBytes, Cfg::kBBytes,
+                   &full[stage]);
         }
         __syncwarp();
-        if (++sb == Cfg::kBStages) sb = 0, pb ^= 1;
+        if (++stage == S) stage = 0, phase ^= 1;
       }
     }
   }
