@@ -65,6 +65,8 @@ SYMBOLS = {
     "dtb200_cost_volume": (C.c_int, [C.POINTER(CostVolumeParams), fp]),
     "dtb200_packed_conv_weight_floats": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dtb200_pack_conv_weight": (C.c_int, [C.c_int32, fp, fp, C.c_int32, C.c_int32, C.c_int32, fp]),
+    "dtb200_packed_conv_weight_floats_srcs": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32]),
+    "dtb200_pack_conv_weight_srcs": (C.c_int, [C.c_int32, fp, fp, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, fp]),
     "dtb200_conv_workspace_bytes": (C.c_uint64, [C.POINTER(ConvParams)]),
     "dtb200_conv2d": (C.c_int, [C.POINTER(ConvParams), fp]),
     "dtb200_conv2d_sequence": (C.c_int, [C.POINTER(ConvParams), C.c_int32, fp]),

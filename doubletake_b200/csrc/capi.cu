@@ -9,8 +9,9 @@ std::atomic<uint64_t> g_launches{0};
 int launch_conv_simt(const dtb200_conv_params& p, int in_c_total, cudaStream_t stream);                  // conv_simt.cu
 int launch_pack_simt(const float* oihw, float* packed, int out_c, int in_c, int ksize, cudaStream_t s);  // conv_simt.cu
 int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t stream);                    // conv_tc.cu
-int launch_pack_tc(const float* oihw, float* packed, int out_c, int in_c, int ksize, cudaStream_t s);    // conv_tc.cu
-uint64_t packed_floats_tc(int out_c, int in_c, int ksize);                                               // conv_tc.cu
+int launch_pack_tc(const float* oihw, float* packed, int out_c, int num_src, const int32_t* src_c, int ksize,
+                   cudaStream_t s);                                                                      // conv_tc.cu
+uint64_t packed_floats_tc(int out_c, int num_src, const int32_t* src_c, int ksize);                      // conv_tc.cu
 uint64_t conv_tc_workspace_bytes(const dtb200_conv_params& p, int in_c_total);                           // conv_tc.cu
 int launch_resample_copy(const dtb200_conv_params& p, cudaStream_t stream);                              // conv_tc.cu
 int conv_tc_debug_set(int flags);                                                                        // conv_tc.cu
@@ -128,15 +129,33 @@ extern "C" int dtb200_exp(const float* src, float* dst, uint64_t count, dtb200_s
 }
 
 extern "C" uint64_t dtb200_packed_conv_weight_floats(int32_t math, int32_t out_c, int32_t in_c, int32_t ksize) {
-  if (math == DTB200_MATH_TC3X) return packed_floats_tc(out_c, in_c, ksize);
+  return dtb200_packed_conv_weight_floats_srcs(math, out_c, 1, &in_c, ksize);
+}
+
+extern "C" uint64_t dtb200_packed_conv_weight_floats_srcs(int32_t math, int32_t out_c, int32_t num_src, const int32_t* src_c,
+                                                          int32_t ksize) {
+  if (!src_c || num_src < 1 || num_src > DTB200_CONV_MAX_SRC) return 0;
+  if (math == DTB200_MATH_TC3X) return packed_floats_tc(out_c, num_src, src_c, ksize);
+  uint64_t in_c = 0;
+  for (int s = 0; s < num_src; ++s) in_c += src_c[s];
   return (uint64_t)out_c * in_c * ksize * ksize;
 }
 
 extern "C" int dtb200_pack_conv_weight(int32_t math, const float* oihw, float* packed, int32_t out_c, int32_t in_c,
                                        int32_t ksize, dtb200_stream_t stream) {
-  if (!oihw || !packed || out_c < 1 || in_c < 1 || (ksize != 1 && ksize != 3))
+  return dtb200_pack_conv_weight_srcs(math, oihw, packed, out_c, 1, &in_c, ksize, stream);
+}
+
+extern "C" int dtb200_pack_conv_weight_srcs(int32_t math, const float* oihw, float* packed, int32_t out_c, int32_t num_src,
+                                            const int32_t* src_c, int32_t ksize, dtb200_stream_t stream) {
+  if (!oihw || !packed || !src_c || out_c < 1 || num_src < 1 || num_src > DTB200_CONV_MAX_SRC || (ksize != 1 && ksize != 3))
     return fail(DTB200_ERR_INVALID, "pack_conv_weight: bad arguments%s");
-  if (math == DTB200_MATH_TC3X) return launch_pack_tc(oihw, packed, out_c, in_c, ksize, (cudaStream_t)stream);
+  int in_c = 0;
+  for (int s = 0; s < num_src; ++s) {
+    if (src_c[s] < 1) return fail(DTB200_ERR_INVALID, "pack_conv_weight: empty source%s");
+    in_c += src_c[s];
+  }
+  if (math == DTB200_MATH_TC3X) return launch_pack_tc(oihw, packed, out_c, num_src, src_c, ksize, (cudaStream_t)stream);
   if (math == DTB200_MATH_EXACT) return launch_pack_simt(oihw, packed, out_c, in_c, ksize, (cudaStream_t)stream);
   return fail(DTB200_ERR_INVALID, "pack_conv_weight: unknown math mode%s");
 }

@@ -1,21 +1,17 @@
 // Fused channels-last convolution on 5th-gen tensor cores (tcgen05, TMEM accumulators), math = TC3X, sm_100a.
 //
-//   dst = act( conv_{k x k, stride}( concat_c[ resample_i(src_i) ] ) + bias (+ residual) )
+//   dst = act( conv_{k x k, stride}( concat_c[ src_i ] ) + bias (+ residual) )
 //
-// Implicit GEMM per CTA: D[128 pixels x BN channels] += A[128 x K] * B[BN x K]^T with K = taps x concatenated input
-// channels, walked in blocks of 32 (4 groups of 8 channels; a group never straddles a source, so torch.cat is free).
+// Implicit GEMM per tile: D[128 pixels x BN channels] += A[128 x K] * B[BN x K]^T, K = taps x 32-channel chunks of the
+// concatenated sources (torch.cat is free: every K block comes from one source).  The 128 pixels are a TW x TH patch of the
+// output map; the A tile of a K block is ONE TMA box (cp.async.bulk.tensor.4d over the NHWC tensor) shifted by the tap
+// offset -- hardware address generation, SWIZZLE_128B placement and zero fill (= the conv's zero padding).
 //
-// Precision: 3xTF32.  Every fp32 operand x is split into big = tf32-truncated x and small = x - big (both exact);
-// per K step three kind::tf32 MMAs accumulate small*big + big*small + big*big in fp32 TMEM.  Per-product error ~2^-21:
-// fp32-class, which the 1e-4 relative depth bar needs through ~20 stacked convs (plain TF32/BF16 does not meet it).
-//
-// Warp roles (288 threads):
-//   warps 0-7  producers: im2col gather (zero padding, concat, x2 up-sampling on load) -> split -> st.shared into the
-//              SWIZZLE_128B K-major A_big / A_small tiles; fence.proxy.async; one mbarrier arrival per warp.
-//              Afterwards the same warps run the epilogue: tcgen05.ld -> bias/residual/activation -> NHWC store.
-//   warp 8     lane 0: cp.async.bulk of the pre-swizzled, pre-split weight tile (UBLKCP, complete_tx on the same
-//              mbarrier), then tcgen05.mma issue (12 per K block) and tcgen05.commit to release the stage.
-// Weights are packed once (dtb200_pack_conv_weight) into the exact shared-memory image of each (N tile, K block).
+// Precision: 3xTF32.  x = big + small with big = tf32-truncated x (the raw fp32 tile itself: kind::tf32 ignores the low
+// 13 mantissa bits) and small = x - big; per K step small*big + big*small + big*big accumulate in fp32 TMEM.
+// Weights are packed once (dtb200_pack_conv_weight_srcs) into the exact shared-memory image of each (N tile, K block).
+#include <cuda.h>
+
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "tc_common.cuh"
@@ -24,68 +20,104 @@ namespace dtb200 {
 
 using namespace tc;
 
-constexpr int kBM = 128;                 // pixels per tile (UMMA M)
-constexpr int kBK = 32;                  // fp32 per K block = one 128-byte swizzled row
-constexpr int kLoadWarps = 4;            // cp.async im2col gather (never fence: they keep many loads in flight)
-constexpr int kSplitWarps = 4;           // smem-only 3xTF32 split + proxy fence
-constexpr int kProducerWarps = kLoadWarps + kSplitWarps;
-constexpr int kEpilogueWarps = 4;
-constexpr int kMmaWarp = kProducerWarps + kEpilogueWarps;      // 12
-constexpr int kAuxWarp = kMmaWarp + 1;                         // 13: weight tiles + row info
-constexpr int kThreads = (kAuxWarp + 1) * 32;                  // 448
+constexpr int kBM = 128;                 // pixels per tile (UMMA M) = TW x TH output pixels
+constexpr int kBK = 32;                  // fp32 per K block = one 128-byte swizzled row = one TMA box row
+constexpr int kEpilogueWarps = 4;        // warps 0-3: TMEM lane quadrant == warp index
+constexpr int kSplitWarps = 4;           // warps 4-7
+constexpr int kMmaWarp = kEpilogueWarps + kSplitWarps;   // 8
+constexpr int kLoadWarp = kMmaWarp + 1;                  // 9: TMA boxes (A) + bulk copies (weight tiles)
+constexpr int kThreads = (kLoadWarp + 1) * 32;           // 320
 constexpr int kATileBytes = kBM * 128;   // 16 KB (one of big / small)
 
 template <int BN>
 struct TcCfg {
   static constexpr int kBTileBytes = BN * 128;
   static constexpr int kBBytes = 2 * kBTileBytes;                    // B_big | B_small
-  static constexpr int kStageBytes = 2 * kATileBytes + kBBytes;      // A_big | A_small | B_big | B_small
+  static constexpr int kStageBytes = 2 * kATileBytes + kBBytes;      // A_big(raw) | A_small | B_big | B_small
   static constexpr int kStages = BN <= 64 ? 4 : 3;
   static constexpr int kTmemCols = 2 * BN;                           // two accumulators
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 2048 /*row info*/ + 512 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
-__host__ __device__ inline int tc_num_kblocks(int in_c, int ksize) { return (in_c * ksize * ksize + kBK - 1) / kBK; }
 __host__ __device__ inline int tc_bn(int out_c) { return (out_c % 128 == 0) ? 128 : 64; }
 
-struct TcWork {  // persistent tile scheduler: item -> (m tile, n tile, K split)
+// K layout shared by the weight packer and the kernel: tap-major; inside a tap the sources in order, each cut into
+// 32-channel chunks (the last chunk of a source may overhang: TMA zero-fills, the packer writes zero weights).
+struct KLayout {
+  int num_src, taps, kb_per_tap, num_kb;
+  int src_c[DTB200_CONV_MAX_SRC], chunk_end[DTB200_CONV_MAX_SRC], c_begin[DTB200_CONV_MAX_SRC];
+};
+__host__ __device__ inline KLayout make_klayout(int num_src, const int32_t* src_c, int ksize) {
+  KLayout k;
+  k.num_src = num_src;
+  k.taps = ksize * ksize;
+  int chunks = 0, cb = 0;
+  for (int s = 0; s < DTB200_CONV_MAX_SRC; ++s) {
+    k.src_c[s] = s < num_src ? src_c[s] : 0;
+    k.c_begin[s] = cb;
+    cb += k.src_c[s];
+    chunks += (k.src_c[s] + kBK - 1) / kBK;
+    k.chunk_end[s] = chunks;
+  }
+  k.kb_per_tap = chunks;
+  k.num_kb = chunks * k.taps;
+  return k;
+}
+__host__ __device__ inline void klayout_decode(const KLayout& k, int kbi, int& tap, int& src, int& c0) {
+  tap = kbi / k.kb_per_tap;
+  const int r = kbi - tap * k.kb_per_tap;
+  src = r < k.chunk_end[0] ? 0 : (r < k.chunk_end[1] ? 1 : 2);
+  const int base = src == 0 ? 0 : (src == 1 ? k.chunk_end[0] : k.chunk_end[1]);
+  c0 = (r - base) * kBK;
+}
+
+struct TcWork {  // persistent tile scheduler: item -> (m tile = (batch, tile row, tile col), n tile, K split)
+  int tw, th, tiles_x, tiles_y;     // pixel tile shape (tw * th == 128) and tile grid per image
   int m_tiles, n_tiles, splits, kb_per_split, num_kb_total;
   long long total;
 };
 
-// Persistent warp-specialised implicit-GEMM conv.  One CTA per SM loops over work items (static stride).
-//   warps 0-7   A producers: im2col gather -> 3xTF32 split -> SWIZZLE_128B tiles (4-deep ring)
-//   warps 8-11  epilogue: TMEM -> bias/residual/activation -> NHWC store (or split-K partials); double-buffered accumulator
-//   warp 12     MMA issuer (one lane): 12 tcgen05.mma per K block, tcgen05.commit frees the A and B stages
-//   warp 13     aux: weight tiles by cp.async.bulk into the same stage/barrier as A (one MMA-side wait per K block), and
-//               the NEXT tile's row info (pixel index + zero-padding tap mask per row) so loaders start tiles without a prologue
+struct TcMaps {
+  CUtensorMap m[DTB200_CONV_MAX_SRC];
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, int c, int x, int y, int b, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tm), "r"(c), "r"(x), "r"(y), "r"(b), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Persistent warp-specialised implicit-GEMM conv, TMA-fed.  One CTA per SM loops over work items (static stride).
+//   warps 0-3  epilogue: TMEM -> bias/residual/activation -> NHWC store (or split-K partials); double-buffered accumulator
+//   warps 4-7  splitters: the raw fp32 tile stays in place as the tf32 "big" operand (the tensor core ignores the low 13
+//              mantissa bits); they add small = x - tf32(x) next to it, fence.proxy.async, arrive
+//   warp 8     MMA issuer (convergent warp, elect.sync): 12 tcgen05.mma per K block, tcgen05.commit frees the stage
+//   warp 9     loader: per K block ONE cp.async.bulk.tensor (TMA) box = 32 channels x (TW x TH) pixels of one source at one
+//              tap, written by hardware in the SWIZZLE_128B layout with zero fill outside the image (= conv padding, also
+//              the channel overhang of sources that are not multiples of 32), plus one cp.async.bulk of the weight tile
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_params p, int in_c_total, long long m_total,
-                                                              TcWork wk, float* __restrict__ partial) {
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_params p, const __grid_constant__ TcMaps maps,
+                                                              KLayout kl, long long m_total, TcWork wk,
+                                                              float* __restrict__ partial) {
   using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* ring = smem;                                                       // S x [A_big|A_small|B_big|B_small]
-  int2* rowinfo = reinterpret_cast<int2*>(ring + S * Cfg::kStageBytes);       // [2][128] {centre pixel index, tap mask}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rowinfo) + 2048);
-  uint64_t* raw_full = bars;            // [S] loaders -> splitters (cp.async completion, 128 arrivals)
-  uint64_t* full = raw_full + S;        // [S] splitters (4) + weight copy (1 + tx) -> MMA: ONE wait per K block
-  uint64_t* empty = full + S;           // [S] MMA (tcgen05.commit) -> loaders, weight loader
+  uint8_t* ring = smem;                                        // S x [A_big|A_small|B_big|B_small]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + S * Cfg::kStageBytes);
+  uint64_t* raw_full = bars;            // [S] TMA box landed (1 arrival + tx)            loader   -> splitters
+  uint64_t* full = raw_full + S;        // [S] small written (4) + weight tile (1 + tx)     -> MMA (one wait per K block)
+  uint64_t* empty = full + S;           // [S] tcgen05.commit                               MMA      -> loader
   uint64_t* acc_full = empty + S;       // [2]
   uint64_t* acc_empty = acc_full + 2;   // [2]
-  uint64_t* ri_full = acc_empty + 2;    // [2] row info of the next tile written
-  uint64_t* ri_empty = ri_full + 2;     // [2] loaders done with it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ri_empty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < S; ++s)
-      mbar_init(&raw_full[s], kLoadWarps * 32), mbar_init(&full[s], kSplitWarps + 1), mbar_init(&empty[s], 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&acc_full[s], 1), mbar_init(&acc_empty[s], kEpilogueWarps);
-      mbar_init(&ri_full[s], 1), mbar_init(&ri_empty[s], kLoadWarps);
-    }
+    for (int s = 0; s < S; ++s) mbar_init(&raw_full[s], 1), mbar_init(&full[s], kSplitWarps + 1), mbar_init(&empty[s], 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&acc_full[s], 1), mbar_init(&acc_empty[s], kEpilogueWarps);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -93,166 +125,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int hw = p.out_h * p.out_w;
 
-  auto decode = [&](long long item, int& m_tile, int& n_tile, int& kb_begin, int& num_kb, int& split) {
+  auto decode = [&](long long item, int& bb, int& y0, int& x0, int& n_tile, int& kb_begin, int& num_kb, int& split) {
     split = (int)(item % wk.splits);
     long long r = item / wk.splits;
     n_tile = (int)(r % wk.n_tiles);
-    m_tile = (int)(r / wk.n_tiles);
+    int m_tile = (int)(r / wk.n_tiles);
+    const int per_img = wk.tiles_x * wk.tiles_y;
+    bb = m_tile / per_img;
+    const int t = m_tile - bb * per_img;
+    y0 = (t / wk.tiles_x) * wk.th;
+    x0 = (t % wk.tiles_x) * wk.tw;
     kb_begin = split * wk.kb_per_split;
     num_kb = min(wk.kb_per_split, wk.num_kb_total - kb_begin);
   };
 
-  if (warp < kLoadWarps) {
-    // ============================================================ A loaders: raw fp32 im2col rows by cp.async
-    SrcView sv[DTB200_CONV_MAX_SRC];
-    int grp_end[DTB200_CONV_MAX_SRC];
-    int acc_g = 0;
-#pragma unroll
-    for (int s = 0; s < DTB200_CONV_MAX_SRC; ++s) {
-      sv[s].ptr = p.src[s];
-      sv[s].c = s < p.num_src ? p.src_c[s] : 0;
-      sv[s].resample = p.src_resample[s];
-      const bool up = sv[s].resample != DTB200_RESAMPLE_NONE;
-      sv[s].h = up ? p.in_h / 2 : p.in_h;
-      sv[s].w = up ? p.in_w / 2 : p.in_w;
-      acc_g += sv[s].c / 8;
-      grp_end[s] = acc_g;
-    }
-    const int groups_per_tap = in_c_total / 8;
-    const int taps = p.ksize * p.ksize;
-    const int pad = p.ksize / 2;
-    const int q = tid & 7;          // 16-byte chunk of the 128-byte row this thread fills
-    const int prow = tid >> 3;      // rows prow + 16*it, it = 0..7
-    uint32_t soff[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = prow + it * 16;
-      soff[it] = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
-    }
-    int stage = 0, phase = 0, use = 0;
-    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
-      int m_tile, n_tile, kb_begin, num_kb, split;
-      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
-      const int rb = use & 1;
-      mbar_wait(&ri_full[rb], (use >> 1) & 1);   // row info of this tile (written one tile ahead by the aux warp)
-      int2 info[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) info[it] = rowinfo[rb * kBM + prow + it * 16];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ri_empty[rb]);  // copied to registers: the buffer can be rewritten
-      // group cursor of this thread's chunk: (tap, group-in-tap), advanced by 4 groups per K block
-      int g_tap, g_r;
-      {
-        const int g = kb_begin * 4 + (q >> 1);
-        g_tap = g / groups_per_tap;
-        g_r = g - g_tap * groups_per_tap;
-      }
-#pragma unroll 1
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const bool g_ok = g_tap < taps;
-        const int tap = g_ok ? g_tap : 0;
-        const int src_i = g_r < grp_end[0] ? 0 : (g_r < grp_end[1] ? 1 : 2);
-        const int base = src_i == 0 ? 0 : (src_i == 1 ? grp_end[0] : grp_end[1]);
-        const int c0 = (g_r - base) * 8 + (q & 1) * 4;
-        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-        SrcView my = sv[0];
-        if (src_i == 1) my = sv[1];
-        if (src_i == 2) my = sv[2];
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* a_big = ring + stage * Cfg::kStageBytes;
-        if (my.resample == DTB200_RESAMPLE_NONE) {
-          const int dpix = (ky - pad) * p.in_w + (kx - pad);
-          const float* bp = my.ptr + c0;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const bool ok = g_ok && ((info[it].y >> tap) & 1);
-            const long long off = ok ? (long long)(info[it].x + dpix) * my.c : 0;
-            cp_async16(a_big + soff[it], bp + off, ok ? 16u : 0u);
-          }
-        } else {
-          // generic path: x2 up-sampling on load (the TC plans normally materialise up-sampled maps instead)
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g_ok && info[it].y != 0) {
-              const long long m = (long long)m_tile * kBM + prow + it * 16;
-              const int bb = (int)(m / hw);
-              const int r = (int)(m - (long long)bb * hw);
-              const int oy = r / p.out_w, ox = r - oy * p.out_w;
-              v = load_input4(my, bb, oy * p.stride + ky - pad, ox * p.stride + kx - pad, p.in_h, p.in_w, c0);
-            }
-            *reinterpret_cast<float4*>(a_big + soff[it]) = v;
-          }
-          __threadfence_block();
-        }
-        cp_async_mbar_arrive(&raw_full[stage]);  // fires when this thread's copies have landed; the thread moves on
-        if (++stage == S) stage = 0, phase ^= 1;
-        g_r += 4;
-        while (g_r >= groups_per_tap) g_r -= groups_per_tap, ++g_tap;
-      }
-    }
-  } else if (warp < kProducerWarps) {
-    // ============================================================ A splitters: small = x - tf32(x), shared memory only
-    // The raw fp32 tile stays in place as the "big" operand: kind::tf32 ignores the low 13 mantissa bits of its
-    // operands (verified on B200: every parity test passes bit-for-bit as with an explicit mask), so big = trunc(x)
-    // needs no store.  Define DTB200_MASK_BIG to write the masked value anyway.
-    const int st = tid - kLoadWarps * 32;
-    const int q = st & 7, prow = st >> 3;
-    uint32_t soff[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = prow + it * 16;
-      soff[it] = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
-    }
-    int stage = 0, phase = 0;
-    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
-      int m_tile, n_tile, kb_begin, num_kb, split;
-      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
-#pragma unroll 1
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&raw_full[stage], phase);
-        uint8_t* a_big = ring + stage * Cfg::kStageBytes;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const float4 v = *reinterpret_cast<const float4*>(a_big + soff[it]);
-          float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
-          float4 small = make_float4(v.x - big.x, v.y - big.y, v.z - big.z, v.w - big.w);
-#ifdef DTB200_MASK_BIG
-          *reinterpret_cast<float4*>(a_big + soff[it]) = big;
-#endif
-          *reinterpret_cast<float4*>(a_big + kATileBytes + soff[it]) = small;
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[stage]);
-        if (++stage == S) stage = 0, phase ^= 1;
-      }
-    }
-  } else if (warp < kMmaWarp) {
+  if (warp < kEpilogueWarps) {
     // ============================================================ epilogue warps
-    const int ew = warp - kProducerWarps;  // == warp % 4 (kProducerWarps is a multiple of 4): TMEM lane quadrant
-    const int row = ew * 32 + lane;
+    const int row = warp * 32 + lane;          // TMEM lane == tile row == (ty, tx) = (row / tw, row % tw)
+    const int ty = row / wk.tw, tx = row - ty * wk.tw;
     int use = 0;
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
-      int m_tile, n_tile, kb_begin, num_kb, split;
-      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
+      int bb, y0, x0, n_tile, kb_begin, num_kb, split;
+      decode(item, bb, y0, x0, n_tile, kb_begin, num_kb, split);
       const int buf = use & 1;
-      const long long m = (long long)m_tile * kBM + row;
-      const bool live = m < m_total;
+      const int oy = y0 + ty, ox = x0 + tx;
+      const bool live = oy < p.out_h && ox < p.out_w;
+      const long long m = ((long long)bb * p.out_h + oy) * p.out_w + ox;   // NHWC pixel index
       const int n_base = n_tile * BN;
       float* dst = nullptr;
       const float* res = nullptr;
       if (partial) {
         dst = partial + ((long long)split * m_total + m) * p.out_c + n_base;
       } else {
-        dst = p.dst + m * p.out_c + n_base;                 // NHWC: pixel index m is the row index
+        dst = p.dst + m * p.out_c + n_base;
         res = p.residual ? p.residual + m * p.out_c + n_base : nullptr;
       }
       mbar_wait(&acc_full[buf], (use >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(ew * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += 32) {
         float v[32];
@@ -267,8 +178,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
             const int n = cc + j;
             float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             if (p.bias) {
-              float4 bb = ld4(p.bias + n_base + n);
-              o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
+              float4 bv = ld4(p.bias + n_base + n);
+              o.x += bv.x, o.y += bv.y, o.z += bv.z, o.w += bv.w;
             }
             if (res) {
               float4 rr = ld4(res + n);
@@ -286,6 +197,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
+  } else if (warp < kMmaWarp) {
+    // ============================================================ splitters: small = x - tf32(x), shared memory only
+    const int st = tid - kEpilogueWarps * 32;
+    const int q = st & 7, prow = st >> 3;
+    uint32_t soff[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = prow + it * 16;
+      soff[it] = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
+    }
+    int stage = 0, phase = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
+      int bb, y0, x0, n_tile, kb_begin, num_kb, split;
+      decode(item, bb, y0, x0, n_tile, kb_begin, num_kb, split);
+#pragma unroll 1
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&raw_full[stage], phase);
+        uint8_t* a_big = ring + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float4 v = *reinterpret_cast<const float4*>(a_big + soff[it]);
+          float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
+          float4 small = make_float4(v.x - big.x, v.y - big.y, v.z - big.z, v.w - big.w);
+          *reinterpret_cast<float4*>(a_big + kATileBytes + soff[it]) = small;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[stage]);
+        if (++stage == S) stage = 0, phase ^= 1;
+      }
+    }
   } else if (warp == kMmaWarp) {
     // ============================================================ MMA issuer (whole warp convergent; elect.sync issues)
     constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
@@ -293,14 +235,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
     const uint32_t ring_u = smem_u32(ring);
     int stage = 0, phase = 0, use = 0;
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
-      int m_tile, n_tile, kb_begin, num_kb, split;
-      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
+      int bb, y0, x0, n_tile, kb_begin, num_kb, split;
+      decode(item, bb, y0, x0, n_tile, kb_begin, num_kb, split);
       const int buf = use & 1;
       mbar_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_u + (uint32_t)(buf * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full[stage], phase);                  // A (split) and B (weight tile) of this K block are in place
+        mbar_wait(&full[stage], phase);                  // A (raw + small) and B (weight tile) of this K block are in place
         tc_fence_after();
         const uint32_t a_big_u = ring_u + stage * Cfg::kStageBytes, a_small_u = a_big_u + kATileBytes;
         const uint32_t b_big_u = a_big_u + 2 * kATileBytes, b_small_u = b_big_u + Cfg::kBTileBytes;
@@ -323,58 +265,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       __syncwarp();
     }
   } else {
-    // ============================================================ aux warp: next tile's row info + weight tiles
+    // ============================================================ loader: TMA boxes (A) + weight tiles (B)
     const int pad = p.ksize / 2;
-    auto write_rowinfo = [&](long long item, int use) {
-      int m_tile, n_tile, kb_begin, num_kb, split;
-      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
-      const int rb = use & 1;
-      mbar_wait(&ri_empty[rb], ((use >> 1) & 1) ^ 1);
-      // lane handles rows 4*lane .. 4*lane+3 (consecutive output pixels): one division, then carry
-      long long m = (long long)m_tile * kBM + lane * 4;
-      int bb = 0, oy = 0, ox = 0;
-      if (m < m_total) {
-        bb = (int)(m / hw);
-        const int r = (int)(m - (long long)bb * hw);
-        oy = r / p.out_w;
-        ox = r - oy * p.out_w;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j, ++m) {
-        int2 info = make_int2(0, 0);
-        if (m < m_total) {
-          const int cy = oy * p.stride, cx = ox * p.stride;
-          int mask = 0, t = 0;
-          for (int ky = 0; ky < p.ksize; ++ky)
-            for (int kx = 0; kx < p.ksize; ++kx, ++t) {
-              const int iy = cy + ky - pad, ix = cx + kx - pad;
-              if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) mask |= 1 << t;
-            }
-          info = make_int2((bb * p.in_h + cy) * p.in_w + cx, mask);
-          if (++ox == p.out_w) {
-            ox = 0;
-            if (++oy == p.out_h) oy = 0, ++bb;
-          }
-        }
-        rowinfo[rb * kBM + lane * 4 + j] = info;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ri_full[rb]);
-    };
-    int stage = 0, phase = 0, use = 0;
-    if ((long long)blockIdx.x < wk.total) write_rowinfo(blockIdx.x, 0);
-    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
-      if (item + gridDim.x < wk.total) write_rowinfo(item + gridDim.x, use + 1);
-      int m_tile, n_tile, kb_begin, num_kb, split;
-      decode(item, m_tile, n_tile, kb_begin, num_kb, split);
+    int stage = 0, phase = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
+      int bb, y0, x0, n_tile, kb_begin, num_kb, split;
+      decode(item, bb, y0, x0, n_tile, kb_begin, num_kb, split);
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) +
                              ((size_t)n_tile * wk.num_kb_total + kb_begin) * Cfg::kBBytes;
       for (int kb = 0; kb < num_kb; ++kb) {
+        int tap, src, c0;
+        klayout_decode(kl, kb_begin + kb, tap, src, c0);
+        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
+          uint8_t* a_big = ring + stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&raw_full[stage], kATileBytes);
+          tma_load_4d(a_big, &maps.m[src], c0, x0 * p.stride + kx - pad, y0 * p.stride + ky - pad, bb, &raw_full[stage]);
           mbar_arrive_expect_tx(&full[stage], Cfg::kBBytes);
-          bulk_g2s(ring + stage * Cfg::kStageBytes + 2 * kATileBytes, wbase + (size_t)kb * Cfg::kBBytes, Cfg::kBBytes,
-                   &full[stage]);
+          bulk_g2s(a_big + 2 * kATileBytes, wbase + (size_t)kb * Cfg::kBBytes, Cfg::kBBytes, &full[stage]);
         }
         __syncwarp();
         if (++stage == S) stage = 0, phase ^= 1;
@@ -390,22 +299,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
 }
 
 // OIHW (out_c, in_c, k, k) -> per (N tile, K block): [B_big tile | B_small tile], each [BN rows][32 fp32] in the
-// SWIZZLE_128B K-major shared-memory image; K flattened tap-major / channel-minor, zero padded to a multiple of 32.
+// SWIZZLE_128B K-major shared-memory image; K blocks follow KLayout (tap-major, per source 32-channel chunks, zero padded).
 __global__ void pack_weight_tc_kernel(const float* __restrict__ oihw, float* __restrict__ packed, int out_c, int in_c,
-                                      int taps, int bn, int num_kb) {
+                                      KLayout kl, int bn) {
   const long long tile_floats = (long long)bn * kBK;
-  const long long total = (long long)(out_c / bn) * num_kb * tile_floats;
+  const long long total = (long long)(out_c / bn) * kl.num_kb * tile_floats;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long t = i / tile_floats;
     int e = (int)(i - t * tile_floats);
-    int n_tile = (int)(t / num_kb), kb = (int)(t - (long long)n_tile * num_kb);
+    int n_tile = (int)(t / kl.num_kb), kbi = (int)(t - (long long)n_tile * kl.num_kb);
     int row = e / kBK, kk = e % kBK;
-    int kflat = kb * kBK + kk;
+    int tap, src, c0;
+    klayout_decode(kl, kbi, tap, src, c0);
+    const int c = c0 + kk;
     float x = 0.f;
-    if (kflat < taps * in_c) {
-      int tap = kflat / in_c, c = kflat - tap * in_c;
-      x = oihw[((long long)(n_tile * bn + row) * in_c + c) * taps + tap];
-    }
+    if (c < kl.src_c[src]) x = oihw[((long long)(n_tile * bn + row) * in_c + kl.c_begin[src] + c) * kl.taps + tap];
     float big = tf32_big(x);
     float* tile = packed + t * 2 * tile_floats;
     uint32_t off = sw128_offset(row, kk) / 4;
@@ -415,30 +323,63 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ oihw, float* __r
 }
 
 int launch_conv_simt(const dtb200_conv_params& p, int in_c_total, cudaStream_t stream);
+int launch_pack_simt(const float* oihw, float* packed, int out_c, int in_c, int ksize, cudaStream_t s);
 
 int conv_tc_debug_set(int) { return DTB200_OK; }  // development hook (knock-out switches live on the experiment branch)
 
-uint64_t packed_floats_tc(int out_c, int in_c, int ksize) {
+uint64_t packed_floats_tc(int out_c, int num_src, const int32_t* src_c, int ksize) {
+  int in_c = 0;
+  for (int s = 0; s < num_src; ++s) in_c += src_c[s];
   if (out_c % 64 != 0) return (uint64_t)out_c * in_c * ksize * ksize;  // heads stay on the SIMT layout
-  return (uint64_t)out_c * tc_num_kblocks(in_c, ksize) * kBK * 2;
+  return (uint64_t)out_c * make_klayout(num_src, src_c, ksize).num_kb * kBK * 2;
 }
 
-int launch_pack_simt(const float* oihw, float* packed, int out_c, int in_c, int ksize, cudaStream_t s);
-
-int launch_pack_tc(const float* oihw, float* packed, int out_c, int in_c, int ksize, cudaStream_t stream) {
+int launch_pack_tc(const float* oihw, float* packed, int out_c, int num_src, const int32_t* src_c, int ksize,
+                   cudaStream_t stream) {
+  int in_c = 0;
+  for (int s = 0; s < num_src; ++s) in_c += src_c[s];
   if (out_c % 64 != 0) return launch_pack_simt(oihw, packed, out_c, in_c, ksize, stream);
-  int bn = tc_bn(out_c), num_kb = tc_num_kblocks(in_c, ksize);
-  long long total = (long long)out_c * num_kb * kBK;
+  KLayout kl = make_klayout(num_src, src_c, ksize);
+  int bn = tc_bn(out_c);
+  long long total = (long long)out_c * kl.num_kb * kBK;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_weight_tc_kernel<<<blocks, 256, 0, stream>>>(oihw, packed, out_c, in_c, ksize * ksize, bn, num_kb);
+  pack_weight_tc_kernel<<<blocks, 256, 0, stream>>>(oihw, packed, out_c, in_c, kl, bn);
   return check_launch("pack_weight_tc_kernel");
 }
 
+// pixel tile shape (tw x th = 128) that covers an out_h x out_w map with the fewest tiles
+static void tc_tile_shape(int out_h, int out_w, int& tw, int& th) {
+  long long best = -1;
+  for (int w = 128; w >= 8; w >>= 1) {
+    const int h = 128 / w;
+    const long long tiles = (long long)((out_w + w - 1) / w) * ((out_h + h - 1) / h);
+    if (best < 0 || tiles < best || (tiles == best && w == 16)) best = tiles, tw = w, th = h;
+  }
+}
+static long long tc_m_tiles(const dtb200_conv_params& p) {
+  int tw, th;
+  tc_tile_shape(p.out_h, p.out_w, tw, th);
+  return (long long)p.batch * ((p.out_w + tw - 1) / tw) * ((p.out_h + th - 1) / th);
+}
+
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* ptr = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess) fn = (TensorMapEncodeFn)ptr;
+  }
+  return fn;
+}
+
 // split-K plan: enough CTAs to fill the machine when the (M, N) grid alone cannot, >= 4 K blocks per split
-static int tc_splits(long long m_total, int out_c, int num_kb) {
+static int tc_splits(long long m_tiles, int out_c, int num_kb) {
   const int bn = tc_bn(out_c);
-  const long long ctas = ((m_total + kBM - 1) / kBM) * (out_c / bn);
+  const long long ctas = m_tiles * (out_c / bn);
   if (ctas >= 148) return 1;
   int splits = (int)((2 * 148 + ctas - 1) / ctas);
   int max_splits = num_kb / 4;
@@ -450,7 +391,8 @@ static int tc_splits(long long m_total, int out_c, int num_kb) {
 uint64_t conv_tc_workspace_bytes(const dtb200_conv_params& p, int in_c_total) {
   if (p.ksize == 0 || p.out_c % 64 != 0) return 0;
   const long long m_total = (long long)p.batch * p.out_h * p.out_w;
-  const int splits = tc_splits(m_total, p.out_c, tc_num_kblocks(in_c_total, p.ksize));
+  (void)in_c_total;
+  const int splits = tc_splits(tc_m_tiles(p), p.out_c, make_klayout(p.num_src, p.src_c, p.ksize).num_kb);
   return splits > 1 ? (uint64_t)splits * m_total * p.out_c * sizeof(float) : 0;
 }
 
@@ -514,15 +456,27 @@ int launch_resample_copy(const dtb200_conv_params& p, cudaStream_t stream) {
 
 int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t stream) {
   if (p.out_c % 64 != 0) return launch_conv_simt(p, in_c_total, stream);  // 1-channel heads: CUDA-core dot product
-  for (int s = 0; s < p.num_src; ++s)
-    if (p.src_c[s] % 8 != 0)
-      return fail(DTB200_ERR_UNSUPPORTED, "conv (tc3x): every source needs a multiple of 8 channels, got %s%lld", "", p.src_c[s]);
+  for (int s = 0; s < p.num_src; ++s) {
+    if (p.src_c[s] % 4 != 0)
+      return fail(DTB200_ERR_UNSUPPORTED, "conv (tc3x): every source needs a multiple of 4 channels, got %s%lld", "", p.src_c[s]);
+    if (p.src_resample[s] != DTB200_RESAMPLE_NONE)
+      return fail(DTB200_ERR_UNSUPPORTED,
+                  "conv (tc3x): x2-resampled sources must be materialised first (ksize = 0 descriptor); ConvPlan does this%s");
+    if (reinterpret_cast<uintptr_t>(p.src[s]) % 16 != 0)
+      return fail(DTB200_ERR_INVALID, "conv (tc3x): source pointers must be 16-byte aligned%s");
+  }
+  TensorMapEncodeFn encode = tensor_map_encoder();
+  if (!encode) return fail(DTB200_ERR_CUDA, "conv (tc3x): cuTensorMapEncodeTiled entry point not available%s");
   const long long m_total = (long long)p.batch * p.out_h * p.out_w;
-  if (m_total * (long long)in_c_total >= (1LL << 31) || (long long)p.batch * p.in_h * p.in_w >= (1LL << 31) / 1024)
-    return fail(DTB200_ERR_UNSUPPORTED, "conv (tc3x): tensor too large for 32-bit pixel indexing%s");
-  const int num_kb = tc_num_kblocks(in_c_total, p.ksize);
+  const KLayout kl = make_klayout(p.num_src, p.src_c, p.ksize);
+  const int num_kb = kl.num_kb;
   const int bn = tc_bn(p.out_c);
-  const int splits = tc_splits(m_total, p.out_c, num_kb);
+  TcWork wk;
+  tc_tile_shape(p.out_h, p.out_w, wk.tw, wk.th);
+  wk.tiles_x = (p.out_w + wk.tw - 1) / wk.tw;
+  wk.tiles_y = (p.out_h + wk.th - 1) / wk.th;
+  wk.m_tiles = p.batch * wk.tiles_x * wk.tiles_y;
+  const int splits = tc_splits(wk.m_tiles, p.out_c, num_kb);
   float* partial = nullptr;
   if (splits > 1) {
     uint64_t need = (uint64_t)splits * m_total * p.out_c * sizeof(float);
@@ -531,14 +485,28 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
                   (long long)need);
     partial = reinterpret_cast<float*>(p.workspace);
   }
-  TcWork wk;
   wk.num_kb_total = num_kb;
   wk.kb_per_split = (num_kb + splits - 1) / splits;
   wk.splits = (num_kb + wk.kb_per_split - 1) / wk.kb_per_split;
-  wk.m_tiles = (int)((m_total + kBM - 1) / kBM);
   wk.n_tiles = p.out_c / bn;
   wk.total = (long long)wk.m_tiles * wk.n_tiles * wk.splits;
   const int zsplits = wk.splits;
+
+  // one 4-D tensor map (C, W, H, B) per source: box = 32 channels x (tw x th) output pixels; for stride 2 the box spans
+  // 2*tw x 2*th input pixels of which every second one is written (elementStrides)
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int s = 0; s < p.num_src; ++s) {
+    const cuuint64_t C = (cuuint64_t)p.src_c[s];
+    cuuint64_t dims[4] = {C, (cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.batch};
+    cuuint64_t strides[3] = {C * 4, (cuuint64_t)p.in_w * C * 4, (cuuint64_t)p.in_h * p.in_w * C * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(wk.tw * p.stride), (cuuint32_t)(wk.th * p.stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)p.stride, (cuuint32_t)p.stride, 1};
+    CUresult r = encode(&maps.m[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.src[s]), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DTB200_ERR_CUDA, "conv (tc3x): cuTensorMapEncodeTiled failed with code %s%lld", "", (long long)r);
+  }
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -551,11 +519,11 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
   if (bn == 128) {
     e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes);
     if (e != cudaSuccess) return fail(DTB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    conv_tc_kernel<128><<<grid, kThreads, TcCfg<128>::kSmemBytes, stream>>>(p, in_c_total, m_total, wk, partial);
+    conv_tc_kernel<128><<<grid, kThreads, TcCfg<128>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial);
   } else {
     e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes);
     if (e != cudaSuccess) return fail(DTB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    conv_tc_kernel<64><<<grid, kThreads, TcCfg<64>::kSmemBytes, stream>>>(p, in_c_total, m_total, wk, partial);
+    conv_tc_kernel<64><<<grid, kThreads, TcCfg<64>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial);
   }
   int rc = check_launch("conv_tc_kernel");
   if (rc != DTB200_OK || !partial) return rc;

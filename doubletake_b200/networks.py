@@ -58,14 +58,17 @@ class ConvPlan:
         self.inputs[name] = f
         return f
 
-    def _pack(self, weight):
-        key = weight.data_ptr()
+    def _pack(self, weight, src_channels):
+        """Device copy of an OIHW weight in the layout the math mode consumes, for this concat split of its inputs."""
+        key = (weight.data_ptr(), tuple(src_channels))
         if key not in self._packed:
             w = L.f32(weight.detach(), self.device)
             oc, ic, k, _ = w.shape
-            n = int(L.lib().dtb200_packed_conv_weight_floats(self.math, oc, ic, k))
+            split = (C.c_int32 * len(src_channels))(*src_channels)
+            n = int(L.lib().dtb200_packed_conv_weight_floats_srcs(self.math, oc, len(src_channels), split, k))
             packed = torch.empty(n, dtype=torch.float32, device=self.device)
-            L.check(L.lib().dtb200_pack_conv_weight(self.math, L.ptr(w), L.ptr(packed), oc, ic, k, L.stream()))
+            L.check(L.lib().dtb200_pack_conv_weight_srcs(self.math, L.ptr(w), L.ptr(packed), oc, len(src_channels), split, k,
+                                                         L.stream()))
             self._packed[key] = packed
             self.keep.append(packed)
         return self._packed[key]
@@ -113,7 +116,7 @@ class ConvPlan:
             total_c += f.c
         if total_c != conv.in_channels:
             raise ValueError(f"conv expects {conv.in_channels} input channels, sources provide {total_c}")
-        op.weight = L.ptr(self._pack(conv.weight))
+        op.weight = L.ptr(self._pack(conv.weight, [f.c for f, _ in srcs]))
         if conv.bias is not None:
             bias = L.f32(conv.bias.detach(), self.device)
             self.keep.append(bias)

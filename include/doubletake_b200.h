@@ -159,6 +159,13 @@ uint64_t dtb200_packed_conv_weight_floats(int32_t math, int32_t out_c, int32_t i
 /* device->device repack of a PyTorch OIHW weight into the layout `math` consumes */
 int dtb200_pack_conv_weight(int32_t math, const float* oihw, float* packed, int32_t out_c, int32_t in_c,
                             int32_t ksize, dtb200_stream_t stream);
+/* Same, for a conv whose input is the concatenation of num_src sources with src_c[] channels each (the layout of the
+ * descriptor it will be used with).  The tensor-core layout cuts every source into its own 32-channel K blocks, so the
+ * packed weights depend on the split; the single-source forms above are the num_src = 1 case. */
+uint64_t dtb200_packed_conv_weight_floats_srcs(int32_t math, int32_t out_c, int32_t num_src, const int32_t* src_c,
+                                               int32_t ksize);
+int dtb200_pack_conv_weight_srcs(int32_t math, const float* oihw, float* packed, int32_t out_c, int32_t num_src,
+                                 const int32_t* src_c, int32_t ksize, dtb200_stream_t stream);
 int dtb200_conv2d(const dtb200_conv_params* p, dtb200_stream_t stream);
 /* Launch a whole network (an array of conv descriptors, in order) from one native call. */
 int dtb200_conv2d_sequence(const dtb200_conv_params* ops, int32_t count, dtb200_stream_t stream);
