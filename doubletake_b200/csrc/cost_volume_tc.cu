@@ -204,75 +204,79 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
       // ---- GEMM1 operand K blocks
       for (int kb = 0; kb < nkb1; ++kb) {
         if (kb == b_meta) producer_bar();  // every view's metadata has been written
+        // The quad (4 lanes of one pixel) has 4 (row, view) combos in this K block: c = 2*rr + hh -> row rr, slot 2kb+hh.
+        // Lane q does the per-combo scalar work of combo q exactly once (projection, sampling setup, masks, depths, source
+        // ray, ray angle, pose constants) and the quad shares the sampling setup by shuffles; then every lane gathers its
+        // own 4 channels for all 4 combos.
         float4 val[2][2];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int slot = 2 * kb + hh;
+        SampleSetup mine;
+        mine.off = 0, mine.mask = 0, mine.w[0] = mine.w[1] = mine.w[2] = mine.w[3] = 0.f;
+        float my_m = 0.f;
+        {
+          const int rr = q >> 1, slot = 2 * kb + (q & 1);
           if (slot < K) {
             const ViewConst& vc = s_vc[slot];
-            const float* sv = p.src_feats_nhwc + ((long long)b * K + slot) * HW * kC;
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-              Projected pr = project_point(vc, X[rr][0], X[rr][1], X[rr][2]);
-              float4 wv = sample_quad(sv, q, pr.u, pr.v, p.height, p.width, invW, invH);
-              float dot = quad_dot(wv, cur);
-              const bool depth_ok = pr.zp > 0.f;
-              const float m = depth_ok ? 1.f : 0.f;
-              dot = DT_MUL(dot, m);
-              val[rr][hh] = wv;
-              float* mrow = meta + (size_t)(rh + 64 * rr) * MS;
-              if (q == 0) {
-                mrow[oMask + slot] = m;
-                mrow[oDepth + slot] = pr.zp;
-                if (lastp[rr] && live) {
-                  bool bounds = (pr.u > 2.f) && (pr.u < (float)(p.width - 2)) && (pr.v > 2.f) && (pr.v < (float)(p.height - 2));
-                  write_masks(p, b, pix, slot, depth_ok, bounds, any_d[rr], any_b[rr]);
-                }
-              } else if (q == 1) {
-                mrow[oDot + slot] = dot;
-                mrow[oComb + slot] = vc.comb;
-                mrow[oRm + slot] = vc.rm;
-                mrow[oTm + slot] = vc.tm;
-              } else {
-                float y0 = DT_SUB(X[rr][0], vc.t[0]), y1 = DT_SUB(X[rr][1], vc.t[1]), y2 = DT_SUB(X[rr][2], vc.t[2]);
-                float sn = DT_MUL(y0, y0);
-                sn = DT_FMA(y1, y1, sn);
-                sn = DT_FMA(y2, y2, sn);
-                float sc = fmaxf(sqrtf(sn), 1e-12f);
-                float rs0 = DT_DIV(y0, sc), rs1 = DT_DIV(y1, sc), rs2 = DT_DIV(y2, sc);
-                if (q == 2) {
-                  mrow[oRaySrc + 3 * slot + 0] = rs0;
-                  mrow[oRaySrc + 3 * slot + 1] = rs1;
-                  mrow[oRaySrc + 3 * slot + 2] = rs2;
-                } else {
-                  float n2 = DT_MUL(rs0, rs0);
-                  n2 = DT_FMA(rs1, rs1, n2);
-                  n2 = DT_FMA(rs2, rs2, n2);
-                  n2 = fmaxf(sqrtf(n2), 1e-5f);
-                  float c0 = DT_MUL(an[rr][0], DT_DIV(rs0, n2)), c1 = DT_MUL(an[rr][1], DT_DIV(rs1, n2)),
-                        c2 = DT_MUL(an[rr][2], DT_DIV(rs2, n2));
-                  mrow[oAngle + slot] = DT_ADD(DT_ADD(c0, c1), c2);
-                }
-              }
+            const float X0 = rr ? X[1][0] : X[0][0], X1 = rr ? X[1][1] : X[0][1], X2 = rr ? X[1][2] : X[0][2];
+            const Projected pr = project_point(vc, X0, X1, X2);
+            mine = sample_setup(pr.u, pr.v, p.height, p.width, invW, invH);
+            const bool depth_ok = pr.zp > 0.f;
+            my_m = depth_ok ? 1.f : 0.f;
+            float* mrow = meta + (size_t)(rh + 64 * rr) * MS;
+            mrow[oMask + slot] = my_m;
+            mrow[oDepth + slot] = pr.zp;
+            mrow[oComb + slot] = vc.comb;
+            mrow[oRm + slot] = vc.rm;
+            mrow[oTm + slot] = vc.tm;
+            if ((rr ? lastp[1] : lastp[0]) && live) {
+              bool bounds = (pr.u > 2.f) && (pr.u < (float)(p.width - 2)) && (pr.v > 2.f) && (pr.v < (float)(p.height - 2));
+              write_masks(p, b, pix, slot, depth_ok, bounds, any_d[0], any_b[0]);  // per-lane accumulators, merged below
             }
-          } else if (slot == K) {
-            val[0][hh] = cur;
-            val[1][hh] = cur;
-          } else {
-            const int m0 = kC * (slot - K - 1) + 4 * q;  // metadata channels m0..m0+3
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-              const float* mrow = meta + (size_t)(rh + 64 * rr) * MS;
-              float4 v;
-              v.x = (m0 + 0 < nmeta) ? mrow[m0 + 0] : 0.f;
-              v.y = (m0 + 1 < nmeta) ? mrow[m0 + 1] : 0.f;
-              v.z = (m0 + 2 < nmeta) ? mrow[m0 + 2] : 0.f;
-              v.w = (m0 + 3 < nmeta) ? mrow[m0 + 3] : 0.f;
-              val[rr][hh] = v;
-            }
+            // source ray normalize(X - t_src) and cos(cur ray, src ray); reciprocal square roots instead of the exact
+            // kernel's IEEE divisions (the operands feed a 3xTF32 GEMM; ~1 ulp differences are irrelevant here)
+            const float y0 = X0 - vc.t[0], y1 = X1 - vc.t[1], y2 = X2 - vc.t[2];
+            const float inv = rsqrtf(fmaxf(y0 * y0 + y1 * y1 + y2 * y2, 1e-24f));
+            const float rs0 = y0 * inv, rs1 = y1 * inv, rs2 = y2 * inv;
+            mrow[oRaySrc + 3 * slot + 0] = rs0;
+            mrow[oRaySrc + 3 * slot + 1] = rs1;
+            mrow[oRaySrc + 3 * slot + 2] = rs2;
+            const float inv2 = rsqrtf(fmaxf(rs0 * rs0 + rs1 * rs1 + rs2 * rs2, 1e-10f));
+            const float a0 = rr ? an[1][0] : an[0][0], a1 = rr ? an[1][1] : an[0][1], a2 = rr ? an[1][2] : an[0][2];
+            mrow[oAngle + slot] = (a0 * rs0 + a1 * rs1 + a2 * rs2) * inv2;
           }
         }
-        mbar_wait(&empty[stage], phase ^ 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int rr = c >> 1, hh = c & 1;
+          const int slot = 2 * kb + hh;
+          if (slot < K) {
+            const int srcl = (lane & ~3) | c;
+            SampleSetup ss;
+            ss.off = __shfl_sync(0xffffffffu, mine.off, srcl);
+            ss.mask = __shfl_sync(0xffffffffu, mine.mask, srcl);
+            ss.w[0] = __shfl_sync(0xffffffffu, mine.w[0], srcl);
+            ss.w[1] = __shfl_sync(0xffffffffu, mine.w[1], srcl);
+            ss.w[2] = __shfl_sync(0xffffffffu, mine.w[2], srcl);
+            ss.w[3] = __shfl_sync(0xffffffffu, mine.w[3], srcl);
+            const float m = __shfl_sync(0xffffffffu, my_m, srcl);
+            const float* sv = p.src_feats_nhwc + ((long long)b * K + slot) * HW * kC;
+            const float4 wv = sample_apply(sv, q, ss, p.width);
+            const float dot = DT_MUL(quad_dot(wv, cur), m);
+            val[rr][hh] = wv;
+            if (q == c) meta[(size_t)(rh + 64 * rr) * MS + oDot + slot] = dot;
+          } else if (slot == K) {
+            val[rr][hh] = cur;
+          } else {
+            const int m0 = kC * (slot - K - 1) + 4 * q;  // metadata channels m0..m0+3
+            const float* mrow = meta + (size_t)(rh + 64 * rr) * MS;
+            float4 v;
+            v.x = (m0 + 0 < nmeta) ? mrow[m0 + 0] : 0.f;
+            v.y = (m0 + 1 < nmeta) ? mrow[m0 + 1] : 0.f;
+            v.z = (m0 + 2 < nmeta) ? mrow[m0 + 2] : 0.f;
+            v.w = (m0 + 3 < nmeta) ? mrow[m0 + 3] : 0.f;
+            val[rr][hh] = v;
+          }
+        }
+        mbar_wait(&empty[stage], phase ^ 1, 10 + kb);
         uint8_t* a_big = stages + stage * kTAStage;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr)
@@ -283,14 +287,18 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
         if (lane == 0) mbar_arrive(&full[stage]);
         if (++stage == kTStages) stage = 0, phase ^= 1;
       }
-      if (q == 0 && p.mask_any) {
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr)
-          if (lastp[rr] && live) p.mask_any[(long long)b * HW + pix] = any_d[rr] && any_b[rr];
+      {
+        // lanes q and q^1 handled the even / odd view slots of row q>>1: merge their any-view flags
+        const int d_other = __shfl_xor_sync(0xffffffffu, (int)any_d[0], 1);  // unconditional: every lane must shuffle
+        const int b_other = __shfl_xor_sync(0xffffffffu, (int)any_b[0], 1);
+        const bool d_all = any_d[0] || (d_other != 0);
+        const bool b_all = any_b[0] || (b_other != 0);
+        const int rr = q >> 1;
+        if ((q & 1) == 0 && p.mask_any && (rr ? lastp[1] : lastp[0]) && live) p.mask_any[(long long)b * HW + pix] = d_all && b_all;
       }
 
       // ---- epilogue-1: D1 -> LeakyReLU(D1 + b1) -> GEMM2 operand K blocks (4 x 32 columns)
-      mbar_wait(d1_full, iter & 1);
+      mbar_wait(d1_full, iter & 1, 20);
       tc_fence_after();
       for (int j = 0; j < 4; ++j) {
         float v[32];
@@ -300,7 +308,7 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = leaky01(v[i] + __ldg(p.b1 + 32 * j + i));
         }
-        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_wait(&empty[stage], phase ^ 1, 30 + j);
         if (mine) {
           uint8_t* a_big = stages + stage * kTAStage;
 #pragma unroll
@@ -317,7 +325,7 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
       }
 
       // ---- epilogue-2: D2 -> LeakyReLU(D2 + b2) . w3 + b3 -> hint MLP -> volume, running arg-max
-      mbar_wait(d2_full, iter & 1);
+      mbar_wait(d2_full, iter & 1, 21);
       tc_fence_after();
       {
         float s = 0.f;
@@ -402,7 +410,7 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
     };
     auto issue_b = [&](long long g) {  // all lanes; one lane issues
       const int sb = (int)(g % SB), pb = (int)((g / SB) & 1);
-      mbar_wait(&b_empty[sb], pb ^ 1);
+      mbar_wait(&b_empty[sb], pb ^ 1, 80);
       if (elect_one()) {
         mbar_arrive_expect_tx(&b_full[sb], kTBStage);
         bulk_g2s(b_ring + (size_t)sb * kTBStage, wtile(g), kTBStage, &b_full[sb]);
@@ -418,8 +426,8 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
         const int sb = (int)(g % SB), pb = (int)((g / SB) & 1);
         const uint32_t a_big_u = stages_u + stage * kTAStage, a_small_u = a_big_u + kTATile;
         const uint32_t b_big_u = b_ring_u + sb * kTBStage, b_small_u = b_big_u + kTBTile;
-        mbar_wait(&full[stage], phase);
-        mbar_wait(&b_full[sb], pb);
+        mbar_wait(&full[stage], phase, 40 + u);
+        mbar_wait(&b_full[sb], pb, 60 + u);
         tc_fence_after();
         const uint32_t dst = (u < nkb1) ? tmem_u : tmem_u + kTHidden;
         const bool first = (u == 0) || (u == nkb1);

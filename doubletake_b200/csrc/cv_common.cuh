@@ -64,29 +64,46 @@ __device__ __forceinline__ Projected project_point(const ViewConst& vc, float X0
   return p;
 }
 
-// F.grid_sample(bilinear, zeros, align_corners=False) of this lane's 4 channels at pixel coords (u,v)
-// (mesh_hint_volume.py:238-249 + ATen grid_sampler_unnormalize; taps accumulate nw, ne, sw, se; OOB/NaN taps skipped).
-__device__ __forceinline__ float4 sample_quad(const float* __restrict__ src_view, int q, float u, float v, int H, int W,
-                                              float invW, float invH) {
+// F.grid_sample(bilinear, zeros, align_corners=False) at pixel coords (u,v), split in two steps so a quad of lanes can
+// share the setup: (1) sampling setup = float offset of the nw texel, the four tap weights (nw, ne, sw, se) and a 4-bit
+// validity mask (zeros padding: OOB / NaN / huge coordinates fail every range test -- GridSampler.cuh behaviour);
+// (2) the gather of this lane's 4 channels.  mesh_hint_volume.py:238-249 + ATen grid_sampler_unnormalize
+// ((g+1)*W-1)/2 -- the division by 2 is written as an exact multiplication by 0.5.
+struct SampleSetup {
+  int off;          // ((y0 * W) + x0) * kC, valid whenever mask != 0
+  float w[4];
+  int mask;         // bit t set: tap t (nw, ne, sw, se) is inside the image
+};
+
+__device__ __forceinline__ SampleSetup sample_setup(float u, float v, int H, int W, float invW, float invH) {
   float gx = DT_SUB(DT_MUL(DT_MUL(2.f, u), invW), 1.f);
   float gy = DT_SUB(DT_MUL(DT_MUL(2.f, v), invH), 1.f);
-  float ix = DT_DIV(DT_SUB(DT_MUL(DT_ADD(gx, 1.f), (float)W), 1.f), 2.f);
-  float iy = DT_DIV(DT_SUB(DT_MUL(DT_ADD(gy, 1.f), (float)H), 1.f), 2.f);
+  float ix = DT_MUL(DT_SUB(DT_MUL(DT_ADD(gx, 1.f), (float)W), 1.f), 0.5f);
+  float iy = DT_MUL(DT_SUB(DT_MUL(DT_ADD(gy, 1.f), (float)H), 1.f), 0.5f);
   float x0f = floorf(ix), y0f = floorf(iy);
   float x1f = DT_ADD(x0f, 1.f), y1f = DT_ADD(y0f, 1.f);
   float wx1 = DT_SUB(ix, x0f), wx0 = DT_SUB(x1f, ix);
   float wy1 = DT_SUB(iy, y0f), wy0 = DT_SUB(y1f, iy);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  // float range tests: NaN / inf / huge coordinates fail every test and sample zero (GridSampler.cuh behaviour)
   bool x0ok = (x0f >= 0.f) && (x0f <= (float)(W - 1));
   bool x1ok = (x1f >= 0.f) && (x1f <= (float)(W - 1));
   bool y0ok = (y0f >= 0.f) && (y0f <= (float)(H - 1));
   bool y1ok = (y1f >= 0.f) && (y1f <= (float)(H - 1));
-  if (!((x0ok || x1ok) && (y0ok || y1ok))) return acc;
-  int x0 = (int)x0f, y0 = (int)y0f;
-  const float* base = src_view + ((long long)y0 * W + x0) * kC + q * 4;
-  auto tap = [&](bool ok, int off, float w) {
-    if (ok) {
+  SampleSetup s;
+  s.mask = (x0ok && y0ok ? 1 : 0) | (x1ok && y0ok ? 2 : 0) | (x0ok && y1ok ? 4 : 0) | (x1ok && y1ok ? 8 : 0);
+  s.off = s.mask ? ((int)y0f * W + (int)x0f) * kC : 0;
+  s.w[0] = DT_MUL(wx0, wy0);
+  s.w[1] = DT_MUL(wx1, wy0);
+  s.w[2] = DT_MUL(wx0, wy1);
+  s.w[3] = DT_MUL(wx1, wy1);
+  return s;
+}
+
+__device__ __forceinline__ float4 sample_apply(const float* __restrict__ src_view, int q, const SampleSetup& s, int W) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s.mask == 0) return acc;
+  const float* base = src_view + s.off + q * 4;
+  auto tap = [&](int bit, int off, float w) {
+    if (s.mask & bit) {
       float4 t = __ldg(reinterpret_cast<const float4*>(base + off));
       acc.x = DT_FMA(t.x, w, acc.x);
       acc.y = DT_FMA(t.y, w, acc.y);
@@ -94,11 +111,16 @@ __device__ __forceinline__ float4 sample_quad(const float* __restrict__ src_view
       acc.w = DT_FMA(t.w, w, acc.w);
     }
   };
-  tap(x0ok && y0ok, 0, DT_MUL(wx0, wy0));
-  tap(x1ok && y0ok, kC, DT_MUL(wx1, wy0));
-  tap(x0ok && y1ok, W * kC, DT_MUL(wx0, wy1));
-  tap(x1ok && y1ok, (W + 1) * kC, DT_MUL(wx1, wy1));
+  tap(1, 0, s.w[0]);
+  tap(2, kC, s.w[1]);
+  tap(4, W * kC, s.w[2]);
+  tap(8, (W + 1) * kC, s.w[3]);
   return acc;
+}
+
+__device__ __forceinline__ float4 sample_quad(const float* __restrict__ src_view, int q, float u, float v, int H, int W,
+                                              float invW, float invH) {
+  return sample_apply(src_view, q, sample_setup(u, v, H, W, invW, invH), W);
 }
 
 // 16-channel dot product of the warped source texel with the current-view feature; result in all 4 quad lanes.
