@@ -299,12 +299,13 @@ def run_b200(args):
 
 def ncu_traffic():
     """DRAM bytes per step per kernel family from the committed ncu launch list of this same command
-    (profiles/r01_traffic.json, produced by tools/traffic_from_launches.py); None when absent."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(path):
+    (profiles/r*_traffic.json, produced by tools/traffic_from_launches.py; the newest file wins); {} when absent."""
+    import glob
+    out = {}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json"))):
         with open(path) as f:
-            return json.load(f)
-    return {}
+            out.update(json.load(f))
+    return out
 
 
 def kernel_rooflines(model, dev_sets, cfg, flush, L, reps=5):

@@ -7,7 +7,7 @@ import csv
 import json
 import sys
 
-path, math, steps = sys.argv[1], sys.argv[2], int(sys.argv[3])
+path, math, steps = sys.argv[1], sys.argv[2], float(sys.argv[3])
 rows = list(csv.reader(open(path)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 hdr = rows[hi]
