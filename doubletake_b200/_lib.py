@@ -70,6 +70,12 @@ SYMBOLS = {
     "dtb200_conv_workspace_bytes": (C.c_uint64, [C.POINTER(ConvParams)]),
     "dtb200_conv2d": (C.c_int, [C.POINTER(ConvParams), fp]),
     "dtb200_conv2d_sequence": (C.c_int, [C.POINTER(ConvParams), C.c_int32, fp]),
+    "dtb200_conv_graph_create": (C.c_int, [C.POINTER(ConvParams), C.c_int32, C.c_int32, C.POINTER(fp)]),
+    "dtb200_conv_graph_launch": (C.c_int, [fp, fp]),
+    "dtb200_conv_graph_info": (C.c_int, [fp] + [C.POINTER(C.c_int32)] * 5),
+    "dtb200_conv_graph_destroy": (None, [fp]),
+    "dtb200_conv_graph_analyze": (C.c_int, [C.POINTER(ConvParams), C.c_int32, C.c_int32] + [C.POINTER(C.c_int32)] * 4
+                                  + [C.c_int32]),
     "dtb200_relative_poses": (C.c_int, [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, fp]),
     "dtb200_exp": (C.c_int, [fp, fp, C.c_uint64, fp]),
 }

@@ -11,6 +11,7 @@
 // 13 mantissa bits) and small = x - big; per K step small*big + big*small + big*big accumulate in fp32 TMEM.
 // Weights are packed once (dtb200_pack_conv_weight_srcs) into the exact shared-memory image of each (N tile, K block).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "conv_common.cuh"
@@ -29,13 +30,18 @@ constexpr int kLoadWarp = kMmaWarp + 1;                  // 9: TMA boxes (A) + b
 constexpr int kThreads = (kLoadWarp + 1) * 32;           // 320
 constexpr int kATileBytes = kBM * 128;   // 16 KB (one of big / small)
 
-template <int BN>
+// kMerged (BN = 64): the weight tile image [B_big | B_small] is 128 contiguous K-major rows, so ONE N=128 MMA computes
+// A_big x [B_big | B_small]^T into two 64-column halves of a 128-column accumulator and a second N=64 MMA adds
+// A_small x B_big^T to the first half; the epilogue sums the halves.  2 MMAs (64 + 48 clk, 14 KB of operand reads) per
+// K step instead of 3 (3 x 48 clk, 18 KB): the N=64 tiles are bound by shared-memory operand bandwidth.
+template <int BN, bool kMerged>
 struct TcCfg {
   static constexpr int kBTileBytes = BN * 128;
   static constexpr int kBBytes = 2 * kBTileBytes;                    // B_big | B_small
   static constexpr int kStageBytes = 2 * kATileBytes + kBBytes;      // A_big(raw) | A_small | B_big | B_small
   static constexpr int kStages = BN <= 64 ? 4 : 3;
-  static constexpr int kTmemCols = 2 * BN;                           // two accumulators
+  static constexpr int kAccCols = kMerged ? 2 * BN : BN;             // TMEM columns of one accumulator
+  static constexpr int kTmemCols = 2 * kAccCols;                     // two accumulators
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
@@ -97,12 +103,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
 //   warp 9     loader: per K block ONE cp.async.bulk.tensor (TMA) box = 32 channels x (TW x TH) pixels of one source at one
 //              tap, written by hardware in the SWIZZLE_128B layout with zero fill outside the image (= conv padding, also
 //              the channel overhang of sources that are not multiples of 32), plus one cp.async.bulk of the weight tile
-template <int BN>
+template <int BN, bool kMerged>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_params p, const __grid_constant__ TcMaps maps,
                                                               KLayout kl, long long m_total, TcWork wk,
                                                               float* __restrict__ partial) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, kMerged>;
   constexpr int S = Cfg::kStages;
+  static_assert(!kMerged || Cfg::kTmemCols <= 512, "merged accumulators exceed TMEM");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;                                        // S x [A_big|A_small|B_big|B_small]
@@ -163,11 +170,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       }
       mbar_wait(&acc_full[buf], (use >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(warp * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * Cfg::kAccCols) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += 32) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)cc, v);
+        if (kMerged) {  // + A_big x B_small^T, accumulated in the upper half
+          float v2[32];
+          tmem_ld32(taddr + (uint32_t)(BN + cc), v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        }
         if (!live) continue;
         if (partial) {
 #pragma unroll
@@ -231,6 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
   } else if (warp == kMmaWarp) {
     // ============================================================ MMA issuer (whole warp convergent; elect.sync issues)
     constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+    constexpr uint32_t idesc2 = umma_idesc_tf32(kBM, 2 * BN);  // merged: N covers [B_big | B_small]
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t ring_u = smem_u32(ring);
     int stage = 0, phase = 0, use = 0;
@@ -240,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       const int buf = use & 1;
       mbar_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t tmem_d = tmem_u + (uint32_t)(buf * BN);
+      const uint32_t tmem_d = tmem_u + (uint32_t)(buf * Cfg::kAccCols);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase);                  // A (raw + small) and B (weight tile) of this K block are in place
         tc_fence_after();
@@ -252,9 +266,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
             const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes along K inside the swizzled row
             const uint64_t da_b = umma_desc_k128(a_big_u + ko), da_s = umma_desc_k128(a_small_u + ko);
             const uint64_t db_b = umma_desc_k128(b_big_u + ko), db_s = umma_desc_k128(b_small_u + ko);
-            umma_tf32(tmem_d, da_s, db_b, idesc, (kb | ks) != 0);
-            umma_tf32(tmem_d, da_b, db_s, idesc, true);
-            umma_tf32(tmem_d, da_b, db_b, idesc, true);
+            if (kMerged) {
+              umma_tf32(tmem_d, da_b, db_b, idesc2, (kb | ks) != 0);  // [big x big | big x small]
+              umma_tf32(tmem_d, da_s, db_b, idesc, true);             // small x big into the first half
+            } else {
+              umma_tf32(tmem_d, da_s, db_b, idesc, (kb | ks) != 0);
+              umma_tf32(tmem_d, da_b, db_s, idesc, true);
+              umma_tf32(tmem_d, da_b, db_b, idesc, true);
+            }
           }
           umma_commit(&empty[stage]);
         }
@@ -325,7 +344,21 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ oihw, float* __r
 int launch_conv_simt(const dtb200_conv_params& p, int in_c_total, cudaStream_t stream);
 int launch_pack_simt(const float* oihw, float* packed, int out_c, int in_c, int ksize, cudaStream_t s);
 
-int conv_tc_debug_set(int) { return DTB200_OK; }  // development hook (knock-out switches live on the experiment branch)
+// development switches (dtb200_debug_set, or DTB200_CONV_FLAGS in the environment at first use):
+//   bit 0: issue the 64-channel tiles as three N=64 MMAs per K step instead of the merged N=128 + N=64 pair
+//   bit 1: same for the 128-channel tiles (their merged form, N=256 + N=128, takes all 512 TMEM columns)
+static int g_flags = -1;
+static int conv_flags() {
+  if (g_flags < 0) {
+    const char* e = getenv("DTB200_CONV_FLAGS");
+    g_flags = e ? atoi(e) : 0;
+  }
+  return g_flags;
+}
+int conv_tc_debug_set(int flags) {
+  g_flags = flags < 0 ? 0 : flags;
+  return DTB200_OK;
+}
 
 uint64_t packed_floats_tc(int out_c, int num_src, const int32_t* src_c, int ksize) {
   int in_c = 0;
@@ -374,6 +407,24 @@ static TensorMapEncodeFn tensor_map_encoder() {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess) fn = (TensorMapEncodeFn)ptr;
   }
   return fn;
+}
+
+// One-time host state (driver entry point, SM count, opt-in shared memory) resolved outside any stream capture.
+static int g_num_sms = 0;
+void conv_tc_init() {
+  static bool done = false;
+  if (done) return;
+  tensor_map_encoder();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (g_num_sms <= 0) g_num_sms = 148;
+  cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, false>::kSmemBytes);
+  cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, false>::kSmemBytes);
+  cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, true>::kSmemBytes);
+  cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true>::kSmemBytes);
+  cudaGetLastError();
+  done = true;
 }
 
 // split-K plan: enough CTAs to fill the machine when the (M, N) grid alone cannot, >= 4 K blocks per split
@@ -507,23 +558,17 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DTB200_ERR_CUDA, "conv (tc3x): cuTensorMapEncodeTiled failed with code %s%lld", "", (long long)r);
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  conv_tc_init();
+  const int num_sms = g_num_sms;
   const unsigned grid = (unsigned)(wk.total < num_sms ? wk.total : num_sms);
-  cudaError_t e;
-  if (bn == 128) {
-    e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes);
-    if (e != cudaSuccess) return fail(DTB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    conv_tc_kernel<128><<<grid, kThreads, TcCfg<128>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial);
+  if (bn == 128 && !(conv_flags() & 2)) {
+    conv_tc_kernel<128, true><<<grid, kThreads, TcCfg<128, true>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial);
+  } else if (bn == 128) {
+    conv_tc_kernel<128, false><<<grid, kThreads, TcCfg<128, false>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial);
+  } else if (conv_flags() & 1) {
+    conv_tc_kernel<64, false><<<grid, kThreads, TcCfg<64, false>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial);
   } else {
-    e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes);
-    if (e != cudaSuccess) return fail(DTB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    conv_tc_kernel<64><<<grid, kThreads, TcCfg<64>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial);
+    conv_tc_kernel<64, true><<<grid, kThreads, TcCfg<64, true>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial);
   }
   int rc = check_launch("conv_tc_kernel");
   if (rc != DTB200_OK || !partial) return rc;

@@ -13,6 +13,7 @@ it through ONE native call (``dtb200_conv2d_sequence``).  No PyTorch op touches 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -47,6 +48,11 @@ class ConvPlan:
         self._upsampled = {}
         self._array = None
         self.workspace = None
+        self._graph = None
+        # execution mode: "graph" = dependency-DAG CUDA graph (independent layers overlap), "sequence" = stream order
+        self.mode = os.environ.get("DTB200_CONV_MODE", "graph")
+        self.max_lanes = int(os.environ.get("DTB200_CONV_LANES", "8"))
+        self.workspace_slots = int(os.environ.get("DTB200_CONV_WS_SLOTS", "6"))
 
     def new(self, b, h, w, c):
         t = torch.empty((b, h, w, c), dtype=torch.float32, device=self.device)
@@ -132,13 +138,44 @@ class ConvPlan:
         return out
 
     def finalize(self):
-        need = max([int(L.lib().dtb200_conv_workspace_bytes(C.byref(op))) for op in self.ops] + [0])
-        if need:
-            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
-            for op in self.ops:
-                op.workspace, op.workspace_bytes = L.ptr(self.workspace), need
+        """Hand out split-K scratch and freeze the descriptor array.  Ops that need scratch rotate over a small pool of
+        slots: two ops on the same slot are serialised by the graph's dependency analysis, ops on different slots may
+        overlap (in "sequence" mode one slot serves everything)."""
+        needs = [int(L.lib().dtb200_conv_workspace_bytes(C.byref(op))) for op in self.ops]
+        need = (max(needs + [0]) + 255) // 256 * 256
+        users = [i for i, n in enumerate(needs) if n]
+        if users:
+            slots = max(1, min(self.workspace_slots, len(users))) if self.mode == "graph" else 1
+            self.workspace = torch.empty(need * slots, dtype=torch.uint8, device=self.device)
+            base = L.ptr(self.workspace)
+            for n, i in enumerate(users):
+                self.ops[i].workspace, self.ops[i].workspace_bytes = base + (n % slots) * need, need
         self._array = (L.ConvParams * len(self.ops))(*self.ops)
         return self
+
+    def analyze(self):
+        """Host-side dependency analysis of the plan (no launch): per-op lane, level and direct dependencies."""
+        n = len(self.ops)
+        lane, level, off = (C.c_int32 * n)(), (C.c_int32 * n)(), (C.c_int32 * (n + 1))()
+        cap = n * 8
+        deps = (C.c_int32 * cap)()
+        L.check(L.lib().dtb200_conv_graph_analyze(self._array, n, self.max_lanes, lane, level, off, deps, cap))
+        return [dict(lane=lane[i], level=level[i], deps=list(deps[off[i]:off[i + 1]])) for i in range(n)]
+
+    def graph_info(self):
+        if self._graph is None:
+            return None
+        v = [C.c_int32() for _ in range(5)]
+        L.check(L.lib().dtb200_conv_graph_info(self._graph, *[C.byref(x) for x in v]))
+        return dict(zip(("ops", "kernels", "edges", "lanes", "depth"), (x.value for x in v)))
+
+    def __del__(self):
+        g, self._graph = getattr(self, "_graph", None), None
+        if g is not None:
+            try:
+                L.lib().dtb200_conv_graph_destroy(g)
+            except Exception:
+                pass
 
     def flops(self):
         total = 0
@@ -159,7 +196,15 @@ class ConvPlan:
             L.nchw_to_nhwc(x, out=f.t)
 
     def run(self):
-        L.check(L.lib().dtb200_conv2d_sequence(self._array, len(self.ops), L.stream()))
+        if self.mode != "graph":
+            L.check(L.lib().dtb200_conv2d_sequence(self._array, len(self.ops), L.stream()))
+            return
+        if self._graph is None:
+            # weights were packed on the current stream; the capture itself executes nothing
+            g = L.fp()
+            L.check(L.lib().dtb200_conv_graph_create(self._array, len(self.ops), self.max_lanes, C.byref(g)))
+            self._graph = g
+        L.check(L.lib().dtb200_conv_graph_launch(self._graph, L.stream()))
 
 
 def _nchw_out(f: Feature):

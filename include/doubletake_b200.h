@@ -170,6 +170,28 @@ int dtb200_conv2d(const dtb200_conv_params* p, dtb200_stream_t stream);
 /* Launch a whole network (an array of conv descriptors, in order) from one native call. */
 int dtb200_conv2d_sequence(const dtb200_conv_params* ops, int32_t count, dtb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Compiled networks.  A descriptor array is analysed into its dependency DAG (from the buffers every op reads and
+ * writes: sources, residual, dst, split-K workspace) and captured once into a CUDA graph in which independent layers
+ * -- the parallel right/diag/up blocks of a DepthDecoderPP column (modules/networks.py:65-85), a BasicBlock's skip
+ * projection next to its conv1 (modules/layers.py:77-94) -- run concurrently, so the idle SMs of one layer's last
+ * tile round are taken by the next layer.  Results are bit-identical to dtb200_conv2d_sequence.
+ * The descriptors' buffers (and packed weights) must stay allocated and in place while the graph is alive; ops that
+ * may overlap need disjoint split-K workspaces (any two ops whose workspace ranges intersect are serialised).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct dtb200_conv_graph dtb200_conv_graph;
+/* max_lanes: upper bound on concurrently runnable branches (capture streams); 1 = a linear graph */
+int dtb200_conv_graph_create(const dtb200_conv_params* ops, int32_t count, int32_t max_lanes, dtb200_conv_graph** out);
+int dtb200_conv_graph_launch(dtb200_conv_graph* g, dtb200_stream_t stream);
+/* any pointer may be NULL: descriptors, kernels per replay, graph edges, lanes used, longest dependency chain */
+int dtb200_conv_graph_info(const dtb200_conv_graph* g, int32_t* ops, int32_t* kernels, int32_t* edges, int32_t* lanes,
+                           int32_t* depth);
+void dtb200_conv_graph_destroy(dtb200_conv_graph* g);
+/* Host-only part of the above (no CUDA call; usable without a GPU): lane and dependency level of every op and the
+ * transitively reduced dependency lists in CSR form (dep_offsets has count+1 entries).  Output pointers may be NULL. */
+int dtb200_conv_graph_analyze(const dtb200_conv_params* ops, int32_t count, int32_t max_lanes, int32_t* lane_of,
+                              int32_t* level_of, int32_t* dep_offsets, int32_t* deps, int32_t deps_capacity);
+
 /* Relative camera poses of DepthModel.forward (experiment_modules/doubletake_model.py:341-349):
  *   src_cam_T_cur_cam[b,k] = src_cam_T_world[b,k] @ cur_world_T_cam[b]   (the managers' src_extrinsics)
  *   cur_cam_T_src_cam[b,k] = cur_cam_T_world[b] @ src_world_T_cam[b,k]   (the managers' src_poses)

@@ -108,3 +108,31 @@ def test_single_conv_features_against_torch(math):
         got = o.t.cpu().permute(0, 3, 1, 2)
         assert got.shape == r.shape
         assert hp.rel_err(got, r) < FEAT_TOL[math]
+
+
+@pytest.mark.parametrize("math", ["exact", "tc3x"])
+def test_graph_mode_is_bit_identical_to_stream_order(math, monkeypatch):
+    """The compiled-network runtime (csrc/conv_graph.cu) only reorders INDEPENDENT launches: outputs must not change by a
+    bit against the same descriptors launched in program order, run after run."""
+    fx = hp.load("net_pp_d64")
+    cfg, cv, priors, seed = hp.network_case_inputs(fx, "unet_pp")
+    outs = {}
+    for mode in ("sequence", "graph"):
+        monkeypatch.setenv("DTB200_CONV_MODE", mode)
+        enc, dec, _, _ = build(fx, "unet_pp", cfg.planes, cfg.prior_ch, seed, math=math)
+        runs = []
+        for _ in range(3):
+            cvf = enc(cv.to(DEV), [p.to(DEV) for p in priors[1:]])
+            out = dec([priors[0].to(DEV)] + cvf)
+            runs.append([f.clone() for f in cvf] + [out[f"log_depth_pred_s{i}_b1hw"].clone() for i in range(4)])
+        for r in runs[1:]:
+            assert all(torch.equal(a, b) for a, b in zip(runs[0], r)), mode
+        outs[mode] = runs[0]
+        plan = next(iter(dec._plans.values()))
+        if mode == "graph":
+            info = plan.graph_info()
+            assert info["ops"] == len(plan.ops) and info["kernels"] >= info["ops"]
+            assert info["lanes"] > 1 and info["depth"] < info["ops"]
+        else:
+            assert plan.graph_info() is None
+    assert all(torch.equal(a, b) for a, b in zip(outs["sequence"], outs["graph"]))
