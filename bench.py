@@ -204,10 +204,10 @@ def run_b200(args):
         return depth
 
     def step_e2e(i):
+        # pinned HOST dicts go straight into the public API: forward() stages them on its copy stream (matching features
+        # and hint first, prior maps while the cost volume runs) -- every byte is copied inside the timed region
         cur, src = host_sets[i % n_sets]
-        cur_d = tree_map(lambda t: t.to(dev, non_blocking=True), cur)
-        src_d = tree_map(lambda t: t.to(dev, non_blocking=True), src)
-        out = model("test", cur_d, src_d, return_mask=True)
+        out = model("test", cur, src, return_mask=True)
         depth = out["depth_pred_s0_b1hw"]
         if world > 1:
             depth = sharding.gather_depth_maps(depth, frames_per_step)

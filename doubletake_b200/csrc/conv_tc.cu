@@ -26,24 +26,42 @@ constexpr int kBK = 32;                  // fp32 per K block = one 128-byte swiz
 constexpr int kEpilogueWarps = 4;        // warps 0-3: TMEM lane quadrant == warp index
 constexpr int kSplitWarps = 4;           // warps 4-7
 constexpr int kMmaWarp = kEpilogueWarps + kSplitWarps;   // 8
-constexpr int kLoadWarp = kMmaWarp + 1;                  // 9: TMA boxes (A) + bulk copies (weight tiles)
-constexpr int kThreads = (kLoadWarp + 1) * 32;           // 320
+constexpr int kLoadWarp = kMmaWarp + 1;                  // 9: TMA boxes (A); 10: bulk copies (weight tiles)
+constexpr int kThreads = (kLoadWarp + 2) * 32;           // 352
 constexpr int kATileBytes = kBM * 128;   // 16 KB (one of big / small)
 
 // kMerged (BN = 64): the weight tile image [B_big | B_small] is 128 contiguous K-major rows, so ONE N=128 MMA computes
 // A_big x [B_big | B_small]^T into two 64-column halves of a 128-column accumulator and a second N=64 MMA adds
 // A_small x B_big^T to the first half; the epilogue sums the halves.  2 MMAs (64 + 48 clk, 14 KB of operand reads) per
 // K step instead of 3 (3 x 48 clk, 18 KB): the N=64 tiles are bound by shared-memory operand bandwidth.
-template <int BN, bool kMerged>
+template <int BN, bool kMerged, int kS = (BN <= 64 ? 4 : 3)>
 struct TcCfg {
   static constexpr int kBTileBytes = BN * 128;
   static constexpr int kBBytes = 2 * kBTileBytes;                    // B_big | B_small
   static constexpr int kStageBytes = 2 * kATileBytes + kBBytes;      // A_big(raw) | A_small | B_big | B_small
-  static constexpr int kStages = BN <= 64 ? 4 : 3;
+  static constexpr int kStages = kS;
   static constexpr int kAccCols = kMerged ? 2 * BN : BN;             // TMEM columns of one accumulator
   static constexpr int kTmemCols = 2 * kAccCols;                     // two accumulators
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
+
+// development switches (dtb200_debug_set, or DTB200_CONV_FLAGS in the environment at first use):
+//   bit 0: issue the 64-channel tiles as three N=64 MMAs per K step instead of the merged N=128 + N=64 pair
+//   bit 1: same for the 128-channel tiles (their merged form, N=256 + N=128, takes all 512 TMEM columns)
+//   bit 2: previous split-K rule (many short items) instead of the round-count cost model
+//   bits 8..12: timing knock-outs of the tensor-core conv pipeline (results are WRONG; tools/conv_bench.py --debug)
+static int g_flags = -1;
+static int conv_flags() {
+  if (g_flags < 0) {
+    const char* e = getenv("DTB200_CONV_FLAGS");
+    g_flags = e ? atoi(e) : 0;
+  }
+  return g_flags;
+}
+int conv_tc_debug_set(int flags) {
+  g_flags = flags < 0 ? 0 : flags;
+  return DTB200_OK;
+}
 
 __host__ __device__ inline int tc_bn(int out_c) { return (out_c % 128 == 0) ? 128 : 64; }
 
@@ -95,6 +113,27 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// dbg bit 5 (flag value 32 << 8): per-role cycle accounting, printed by CTA 0 (development aid, see tools/conv_bench.py)
+struct RoleProf {
+  long long t0 = 0, waited = 0;
+  int n = 0;
+};
+__device__ __forceinline__ void prof_wait(uint64_t* bar, uint32_t parity, bool on, RoleProf& pr) {
+  if (!on) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const long long a = clock64();
+  mbar_wait(bar, parity);
+  pr.waited += clock64() - a;
+  ++pr.n;
+}
+__device__ __forceinline__ void prof_report(const char* role, bool on, const RoleProf& pr) {
+  if (on && blockIdx.x == 0 && (threadIdx.x & 31) == 0)
+    printf("role %-8s warp %2d: %8lld clk in loop, %8lld clk waiting, %5d waits\n", role, (int)(threadIdx.x >> 5),
+           clock64() - pr.t0, pr.waited, pr.n);
+}
+
 // Persistent warp-specialised implicit-GEMM conv, TMA-fed.  One CTA per SM loops over work items (static stride).
 //   warps 0-3  epilogue: TMEM -> bias/residual/activation -> NHWC store (or split-K partials); double-buffered accumulator
 //   warps 4-7  splitters: the raw fp32 tile stays in place as the tf32 "big" operand (the tensor core ignores the low 13
@@ -103,11 +142,11 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
 //   warp 9     loader: per K block ONE cp.async.bulk.tensor (TMA) box = 32 channels x (TW x TH) pixels of one source at one
 //              tap, written by hardware in the SWIZZLE_128B layout with zero fill outside the image (= conv padding, also
 //              the channel overhang of sources that are not multiples of 32), plus one cp.async.bulk of the weight tile
-template <int BN, bool kMerged>
+template <int BN, bool kMerged, int kS = (BN <= 64 ? 4 : 3)>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_params p, const __grid_constant__ TcMaps maps,
                                                               KLayout kl, long long m_total, TcWork wk,
-                                                              float* __restrict__ partial) {
-  using Cfg = TcCfg<BN, kMerged>;
+                                                              float* __restrict__ partial, int dbg) {
+  using Cfg = TcCfg<BN, kMerged, kS>;
   constexpr int S = Cfg::kStages;
   static_assert(!kMerged || Cfg::kTmemCols <= 512, "merged accumulators exceed TMEM");
   extern __shared__ uint8_t smem_raw[];
@@ -120,11 +159,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
   uint64_t* acc_full = empty + S;       // [2]
   uint64_t* acc_empty = acc_full + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  long long* stamp = reinterpret_cast<long long*>(tmem_slot + 2);  // [2][S] profiling time stamps (dbg bit 5 only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(&raw_full[s], 1), mbar_init(&full[s], kSplitWarps + 1), mbar_init(&empty[s], 1);
+    for (int s = 0; s < S; ++s) mbar_init(&raw_full[s], 1), mbar_init(&full[s], ((dbg & 64) ? kSplitWarps : kSplitWarps / 2) + 1), mbar_init(&empty[s], 1);
     for (int s = 0; s < 2; ++s) mbar_init(&acc_full[s], 1), mbar_init(&acc_empty[s], kEpilogueWarps);
+    for (int s = 0; s < 2 * S; ++s) stamp[s] = 0;
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -132,6 +173,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool prof = (dbg & 32) != 0;
+  RoleProf pr, pr2, pr3;
+  if (prof) pr.t0 = pr2.t0 = clock64();
 
   auto decode = [&](long long item, int& bb, int& y0, int& x0, int& n_tile, int& kb_begin, int& num_kb, int& split) {
     split = (int)(item % wk.splits);
@@ -168,11 +212,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         dst = p.dst + m * p.out_c + n_base;
         res = p.residual ? p.residual + m * p.out_c + n_base : nullptr;
       }
-      mbar_wait(&acc_full[buf], (use >> 1) & 1);
+      prof_wait(&acc_full[buf], (use >> 1) & 1, prof, pr);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(buf * Cfg::kAccCols) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += 32) {
+        float r[32];
+        const bool use_res = res != nullptr && live && !(dbg & 16);
+        if (use_res) {  // residual row segment first: its latency overlaps the TMEM loads
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) ldg256(res + cc + j, r + j);
+        }
         float v[32];
         tmem_ld32(taddr + (uint32_t)cc, v);
         if (kMerged) {  // + A_big x B_small^T, accumulated in the upper half
@@ -181,30 +231,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += v2[j];
         }
-        if (!live) continue;
-        if (partial) {
+        if (!live || (dbg & 16)) continue;
+        if (!partial) {
+          if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = cc + j;
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.bias) {
-              float4 bv = ld4(p.bias + n_base + n);
-              o.x += bv.x, o.y += bv.y, o.z += bv.z, o.w += bv.w;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = ld4(p.bias + n_base + cc + j);
+              v[j] += bv.x, v[j + 1] += bv.y, v[j + 2] += bv.z, v[j + 3] += bv.w;
             }
-            if (res) {
-              float4 rr = ld4(res + n);
-              o.x += rr.x, o.y += rr.y, o.z += rr.z, o.w += rr.w;
-            }
-            o.x = activate(o.x, p.act, p.act_slope);
-            o.y = activate(o.y, p.act, p.act_slope);
-            o.z = activate(o.z, p.act, p.act_slope);
-            o.w = activate(o.w, p.act, p.act_slope);
-            *reinterpret_cast<float4*>(dst + n) = o;
           }
+          if (use_res) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += r[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.act, p.act_slope);
         }
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) stg256(dst + cc + j, v + j);
       }
       tc_fence_before();
       __syncwarp();
@@ -212,60 +256,87 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
     }
   } else if (warp < kMmaWarp) {
     // ============================================================ splitters: small = x - tf32(x), shared memory only
-    const int st = tid - kEpilogueWarps * 32;
+    // Two groups of two warps take alternate K blocks: the per-K-block cost of a group (barrier wake-up, shared-memory
+    // round trip, proxy fence) is latency, not work, so two blocks are in flight at once.
+    // A stage is always split by the same warps (a parity wait must observe every phase of its barrier).
+    const bool split_all = (dbg & 64) != 0;  // experiment: all four warps on every K block instead of two groups
+    const int group = split_all ? 0 : (warp - kEpilogueWarps) >> 1;
+    const int st = tid - (kEpilogueWarps + 2 * group) * 32;  // 0..63 inside a group (0..127 with split_all)
     const int q = st & 7, prow = st >> 3;
-    uint32_t soff[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = prow + it * 16;
-      soff[it] = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
-    }
+    const uint32_t ring_u = smem_u32(ring);
+    auto soff = [&](int row) { return (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4); };
+    auto split4 = [&](uint32_t a_big_u, const float4& x, int row) {
+      const float4 big = make_float4(tf32_big(x.x), tf32_big(x.y), tf32_big(x.z), tf32_big(x.w));
+      sts128(a_big_u + kATileBytes + soff(row), make_float4(x.x - big.x, x.y - big.y, x.z - big.z, x.w - big.w));
+    };
     int stage = 0, phase = 0;
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
       int bb, y0, x0, n_tile, kb_begin, num_kb, split;
       decode(item, bb, y0, x0, n_tile, kb_begin, num_kb, split);
 #pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&raw_full[stage], phase);
-        uint8_t* a_big = ring + stage * Cfg::kStageBytes;
+        if (split_all || (stage & 1) == group) {
+          prof_wait(&raw_full[stage], phase, prof, pr);
+          if (prof && st == 0) pr2.waited += clock64() - stamp[stage], ++pr2.n;  // TMA issue -> box landed and seen
+          if (!(dbg & 2)) {
+            // all loads first (explicit ld.shared: the generic-pointer form serialises load -> store -> load on possible
+            // aliasing and pays the generic-address translation), then split and store
+            const uint32_t a_big_u = ring_u + (uint32_t)(stage * Cfg::kStageBytes);
+            if (split_all) {
+              float4 v[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const float4 v = *reinterpret_cast<const float4*>(a_big + soff[it]);
-          float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
-          float4 small = make_float4(v.x - big.x, v.y - big.y, v.z - big.z, v.w - big.w);
-          *reinterpret_cast<float4*>(a_big + kATileBytes + soff[it]) = small;
+              for (int it = 0; it < 8; ++it) v[it] = lds128(a_big_u + soff(prow + it * 16));
+#pragma unroll
+              for (int it = 0; it < 8; ++it) split4(a_big_u, v[it], prow + it * 16);
+            } else {
+              float4 v[16];
+#pragma unroll
+              for (int it = 0; it < 16; ++it) v[it] = lds128(a_big_u + soff(prow + it * 8));
+#pragma unroll
+              for (int it = 0; it < 16; ++it) split4(a_big_u, v[it], prow + it * 8);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[stage]);
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[stage]);
         if (++stage == S) stage = 0, phase ^= 1;
       }
     }
+    if (prof && st == 0 && blockIdx.x == 0)
+      printf("latency  TMA issue -> splitter sees the box: %lld clk avg over %d\n", pr2.waited / max(pr2.n, 1), pr2.n);
   } else if (warp == kMmaWarp) {
     // ============================================================ MMA issuer (whole warp convergent; elect.sync issues)
     constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
     constexpr uint32_t idesc2 = umma_idesc_tf32(kBM, 2 * BN);  // merged: N covers [B_big | B_small]
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t ring_u = smem_u32(ring);
+    // shared-memory descriptors (tc_common.cuh: umma_desc_k128): the high word is constant, the low word is
+    // (address >> 4) | LBO; per K block only the low word moves (stage base + tile + 32-byte K step), by plain adds
+    constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
+    const uint32_t lo_ring = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
+    auto desc = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
     int stage = 0, phase = 0, use = 0;
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
       int bb, y0, x0, n_tile, kb_begin, num_kb, split;
       decode(item, bb, y0, x0, n_tile, kb_begin, num_kb, split);
       const int buf = use & 1;
-      mbar_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+      prof_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1, prof, pr2);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_u + (uint32_t)(buf * Cfg::kAccCols);
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full[stage], phase);                  // A (raw + small) and B (weight tile) of this K block are in place
+        prof_wait(&full[stage], phase, prof, pr);        // A (raw + small) and B (weight tile) of this K block are in place
         tc_fence_after();
-        const uint32_t a_big_u = ring_u + stage * Cfg::kStageBytes, a_small_u = a_big_u + kATileBytes;
-        const uint32_t b_big_u = a_big_u + 2 * kATileBytes, b_small_u = b_big_u + Cfg::kBTileBytes;
+        if (prof && lane == 0) pr3.waited += clock64() - stamp[stage], ++pr3.n;  // TMA issue -> MMA warp sees `full`
+        const uint32_t lo_a_big = lo_ring + (uint32_t)stage * (Cfg::kStageBytes >> 4);
+        const uint32_t lo_a_small = lo_a_big + (kATileBytes >> 4), lo_b_big = lo_a_big + (2 * kATileBytes >> 4);
+        const uint32_t lo_b_small = lo_b_big + (Cfg::kBTileBytes >> 4);
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t ko = ks * 32;  // 8 tf32 = 32 bytes along K inside the swizzled row
-            const uint64_t da_b = umma_desc_k128(a_big_u + ko), da_s = umma_desc_k128(a_small_u + ko);
-            const uint64_t db_b = umma_desc_k128(b_big_u + ko), db_s = umma_desc_k128(b_small_u + ko);
+            if (dbg & 1) break;
+            const uint32_t ko = ks * 2;  // 8 tf32 = 32 bytes along K inside the swizzled row, in 16-byte units
+            const uint64_t da_b = desc(lo_a_big + ko), da_s = desc(lo_a_small + ko);
+            const uint64_t db_b = desc(lo_b_big + ko), db_s = desc(lo_b_small + ko);
             if (kMerged) {
               umma_tf32(tmem_d, da_b, db_b, idesc2, (kb | ks) != 0);  // [big x big | big x small]
               umma_tf32(tmem_d, da_s, db_b, idesc, true);             // small x big into the first half
@@ -277,6 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
           }
           umma_commit(&empty[stage]);
         }
+        if (prof && lane == 0) stamp[S + stage] = clock64();
         __syncwarp();
         if (++stage == S) stage = 0, phase ^= 1;
       }
@@ -292,22 +364,55 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       decode(item, bb, y0, x0, n_tile, kb_begin, num_kb, split);
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) +
                              ((size_t)n_tile * wk.num_kb_total + kb_begin) * Cfg::kBBytes;
+      // (tap, source, channel chunk) of the item's first K block by division, then advanced incrementally
+      int tap, src, c0;
+      klayout_decode(kl, kb_begin, tap, src, c0);
+      int ky = tap / p.ksize, kx = tap - ky * p.ksize;
       for (int kb = 0; kb < num_kb; ++kb) {
-        int tap, src, c0;
-        klayout_decode(kl, kb_begin + kb, tap, src, c0);
-        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-        mbar_wait(&empty[stage], phase ^ 1);
+        prof_wait(&empty[stage], phase ^ 1, prof, pr);
+        if (prof && warp == kLoadWarp && lane == 0) {
+          const long long now = clock64();
+          if (stamp[S + stage] != 0) pr2.waited += now - stamp[S + stage], ++pr2.n;  // commit issued -> loader sees `empty`
+          stamp[stage] = now;
+        }
         if (elect_one()) {
           uint8_t* a_big = ring + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&raw_full[stage], kATileBytes);
-          tma_load_4d(a_big, &maps.m[src], c0, x0 * p.stride + kx - pad, y0 * p.stride + ky - pad, bb, &raw_full[stage]);
-          mbar_arrive_expect_tx(&full[stage], Cfg::kBBytes);
-          bulk_g2s(a_big + 2 * kATileBytes, wbase + (size_t)kb * Cfg::kBBytes, Cfg::kBBytes, &full[stage]);
+          if (warp == kLoadWarp) {
+            if (dbg & 4) {
+              mbar_arrive(&raw_full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&raw_full[stage], kATileBytes);
+              tma_load_4d(a_big, &maps.m[src], c0, x0 * p.stride + kx - pad, y0 * p.stride + ky - pad, bb, &raw_full[stage]);
+            }
+          } else {
+            if (dbg & 8) {
+              mbar_arrive(&full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], Cfg::kBBytes);
+              bulk_g2s(a_big + 2 * kATileBytes, wbase + (size_t)kb * Cfg::kBBytes, Cfg::kBBytes, &full[stage]);
+            }
+          }
         }
         __syncwarp();
         if (++stage == S) stage = 0, phase ^= 1;
+        c0 += kBK;
+        if (c0 >= (src == 0 ? kl.src_c[0] : (src == 1 ? kl.src_c[1] : kl.src_c[2]))) {
+          c0 = 0;
+          if (++src == kl.num_src) {
+            src = 0;
+            if (++kx == p.ksize) kx = 0, ++ky;
+          }
+        }
       }
     }
+  }
+  if (prof && blockIdx.x == 0 && lane == 0) {
+    if (warp == kMmaWarp) printf("latency  TMA issue -> MMA warp sees full:    %lld clk avg over %d\n", pr3.waited / max(pr3.n, 1), pr3.n);
+    if (warp == kLoadWarp) printf("latency  MMA commit issued -> loader sees empty: %lld clk avg over %d\n", pr2.waited / max(pr2.n, 1), pr2.n);
+  }
+  if (prof) {
+    prof_report(warp < kEpilogueWarps ? "epilogue" : warp < kMmaWarp ? "split" : warp == kMmaWarp ? "mma" : "load", true, pr);
+    if (warp == kMmaWarp) prof_report("mma/acc", true, pr2);
   }
   tc_fence_before();
   __syncthreads();
@@ -343,22 +448,6 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ oihw, float* __r
 
 int launch_conv_simt(const dtb200_conv_params& p, int in_c_total, cudaStream_t stream);
 int launch_pack_simt(const float* oihw, float* packed, int out_c, int in_c, int ksize, cudaStream_t s);
-
-// development switches (dtb200_debug_set, or DTB200_CONV_FLAGS in the environment at first use):
-//   bit 0: issue the 64-channel tiles as three N=64 MMAs per K step instead of the merged N=128 + N=64 pair
-//   bit 1: same for the 128-channel tiles (their merged form, N=256 + N=128, takes all 512 TMEM columns)
-static int g_flags = -1;
-static int conv_flags() {
-  if (g_flags < 0) {
-    const char* e = getenv("DTB200_CONV_FLAGS");
-    g_flags = e ? atoi(e) : 0;
-  }
-  return g_flags;
-}
-int conv_tc_debug_set(int flags) {
-  g_flags = flags < 0 ? 0 : flags;
-  return DTB200_OK;
-}
 
 uint64_t packed_floats_tc(int out_c, int num_src, const int32_t* src_c, int ksize) {
   int in_c = 0;
@@ -422,21 +511,37 @@ void conv_tc_init() {
   cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, false>::kSmemBytes);
   cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, false>::kSmemBytes);
   cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, true>::kSmemBytes);
+  cudaFuncSetAttribute(conv_tc_kernel<64, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true, 2>::kSmemBytes);
+  cudaFuncSetAttribute(conv_tc_kernel<64, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true, 3>::kSmemBytes);
   cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true>::kSmemBytes);
   cudaGetLastError();
   done = true;
 }
 
-// split-K plan: enough CTAs to fill the machine when the (M, N) grid alone cannot, >= 4 K blocks per split
+// split-K plan for maps with fewer (M, N) tiles than SMs.  The kernel is persistent, so time ~ rounds x (K blocks per
+// item + fixed per-item cost) + reduction cost: pick the split count that minimises it (one full round of longer items
+// beats three rounds of short ones).  148 is used as the machine width on purpose: the plan (and the fp32 summation
+// order it implies) must not depend on the device the workspace was sized on.
 static int tc_splits(long long m_tiles, int out_c, int num_kb) {
   const int bn = tc_bn(out_c);
   const long long ctas = m_tiles * (out_c / bn);
-  if (ctas >= 148) return 1;
-  int splits = (int)((2 * 148 + ctas - 1) / ctas);
-  int max_splits = num_kb / 4;
-  if (splits > max_splits) splits = max_splits;
-  if (splits > 32) splits = 32;
-  return splits < 1 ? 1 : splits;
+  if (ctas >= 148 || num_kb < 4) return 1;
+  if (conv_flags() & 4) {  // round-1 rule: >= 2 x 148 items of >= 4 K blocks
+    int splits = (int)((2 * 148 + ctas - 1) / ctas);
+    if (splits > num_kb / 4) splits = num_kb / 4;
+    if (splits > 32) splits = 32;
+    return splits < 1 ? 1 : splits;
+  }
+  int best = 1;
+  double best_cost = 1e30;
+  for (int sp = 1; sp <= 32 && sp * 2 <= num_kb; ++sp) {
+    const int kb_per = (num_kb + sp - 1) / sp;
+    if ((num_kb + kb_per - 1) / kb_per != sp) continue;  // not a distinct partition
+    const long long rounds = (ctas * sp + 147) / 148;
+    const double cost = (double)rounds * (kb_per + 2.0) + (sp > 1 ? 4.0 + 0.5 * sp : 0.0);
+    if (cost < best_cost - 1e-9) best_cost = cost, best = sp;
+  }
+  return best;
 }
 
 uint64_t conv_tc_workspace_bytes(const dtb200_conv_params& p, int in_c_total) {
@@ -516,6 +621,9 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
     if (reinterpret_cast<uintptr_t>(p.src[s]) % 16 != 0)
       return fail(DTB200_ERR_INVALID, "conv (tc3x): source pointers must be 16-byte aligned%s");
   }
+  if (reinterpret_cast<uintptr_t>(p.dst) % 32 != 0 || reinterpret_cast<uintptr_t>(p.residual) % 32 != 0 ||
+      reinterpret_cast<uintptr_t>(p.workspace) % 32 != 0)
+    return fail(DTB200_ERR_INVALID, "conv (tc3x): dst / residual / workspace must be 32-byte aligned (256-bit stores)%s");
   TensorMapEncodeFn encode = tensor_map_encoder();
   if (!encode) return fail(DTB200_ERR_CUDA, "conv (tc3x): cuTensorMapEncodeTiled entry point not available%s");
   const long long m_total = (long long)p.batch * p.out_h * p.out_w;
@@ -561,14 +669,19 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
   conv_tc_init();
   const int num_sms = g_num_sms;
   const unsigned grid = (unsigned)(wk.total < num_sms ? wk.total : num_sms);
+  const int dbg = conv_flags() >> 8;  // timing knock-outs (results are wrong): 1 no MMA, 2 no split, 4 no A box, 8 no B tile, 16 no store
   if (bn == 128 && !(conv_flags() & 2)) {
-    conv_tc_kernel<128, true><<<grid, kThreads, TcCfg<128, true>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial);
+    conv_tc_kernel<128, true><<<grid, kThreads, TcCfg<128, true>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial, dbg);
   } else if (bn == 128) {
-    conv_tc_kernel<128, false><<<grid, kThreads, TcCfg<128, false>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial);
+    conv_tc_kernel<128, false><<<grid, kThreads, TcCfg<128, false>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial, dbg);
   } else if (conv_flags() & 1) {
-    conv_tc_kernel<64, false><<<grid, kThreads, TcCfg<64, false>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial);
+    conv_tc_kernel<64, false><<<grid, kThreads, TcCfg<64, false>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial, dbg);
+  } else if (conv_flags() & 32) {  // experiment: ring depth 2 / 3 instead of 4
+    conv_tc_kernel<64, true, 2><<<grid, kThreads, TcCfg<64, true, 2>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial, dbg);
+  } else if (conv_flags() & 64) {
+    conv_tc_kernel<64, true, 3><<<grid, kThreads, TcCfg<64, true, 3>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial, dbg);
   } else {
-    conv_tc_kernel<64, true><<<grid, kThreads, TcCfg<64, true>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial);
+    conv_tc_kernel<64, true><<<grid, kThreads, TcCfg<64, true>::kSmemBytes, stream>>>(p, maps, kl, m_total, wk, partial, dbg);
   }
   int rc = check_launch("conv_tc_kernel");
   if (rc != DTB200_OK || !partial) return rc;

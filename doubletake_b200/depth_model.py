@@ -106,6 +106,52 @@ class DepthModelCVHint(nn.Module):
             cur, src = allf[:, 0], allf[:, 1:].contiguous()
         return cur, src
 
+    # -------------------------------------------------------------------------------------- host -> device staging
+    _EARLY_KEYS = ("cam_T_world_b44", "world_T_cam_b44", "matching_feats_bchw", "matching_feats_bkchw",
+                   "depth_hint_b1hw", "sampled_weights_b1hw", "depth_hint_mask_b1hw", "image_b3hw")
+
+    def _upload(self, cur_data, src_data, dev):
+        """Inputs that still live in HOST memory (the reference moves the whole batch with ``to_gpu`` before forward,
+        utils/generic_utils.py) are copied on a dedicated copy stream in the order the kernels need them: poses,
+        intrinsics, matching features and hint first (the cost volume waits on event 0), the image-prior feature maps
+        last (only the conv plan waits on event 1).  With pinned buffers the copies of frame i+1 overlap the kernels of
+        frame i, and a frame's prior maps travel while its cost volume is being computed.
+        Returns (cur_data, src_data, (event_early, event_late)) -- events are None when nothing had to move."""
+        def on_host(v):
+            return torch.is_tensor(v) and not v.is_cuda
+
+        trees = (cur_data, src_data)
+        if not any(on_host(x) for d in trees for v in d.values() for x in (v if isinstance(v, (list, tuple)) else [v])):
+            return cur_data, src_data, (None, None)
+        main = torch.cuda.current_stream(dev)
+        copy = self.__dict__.get("_copy_stream")
+        if copy is None or copy.device != dev:
+            copy = self.__dict__["_copy_stream"] = torch.cuda.Stream(dev)
+        out = ({}, {})
+
+        def move(v):
+            if not on_host(v):
+                return v
+            t = v.to(dev, non_blocking=True)
+            t.record_stream(main)
+            return t
+
+        with torch.cuda.stream(copy):
+            late = []
+            for d, o in zip(trees, out):
+                for k, v in d.items():
+                    if isinstance(v, (list, tuple)):
+                        late.append((o, k, v))
+                    elif k in self._EARLY_KEYS or (torch.is_tensor(v) and v.numel() <= 4096):
+                        o[k] = move(v)
+                    else:
+                        late.append((o, k, v))
+            ev_early = copy.record_event()
+            for o, k, v in late:
+                o[k] = [move(x) for x in v] if isinstance(v, (list, tuple)) else move(v)
+            ev_late = copy.record_event()
+        return out[0], out[1], (ev_early, ev_late)
+
     # -------------------------------------------------------------------------------------- hot path
     def _relative_poses(self, cur_data, src_data, dev):
         """doubletake_model.py:341-349 on the device, one kernel."""
@@ -140,6 +186,12 @@ class DepthModelCVHint(nn.Module):
         if phase == "train":
             raise NotImplementedError("doubletake_b200 is an inference engine: the training phase is out of scope")
         ms = self.run_opts.matching_scale
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("doubletake_b200 runs on CUDA only (no CPU fallback): move the model to a CUDA device")
+        cur_data, src_data, (ev_early, ev_late) = self._upload(cur_data, src_data, dev)
+        if ev_early is not None:
+            torch.cuda.current_stream(dev).wait_event(ev_early)
         if "image_prior_feats" in cur_data:
             prior_feats = list(cur_data["image_prior_feats"])
             mcur, msrc = cur_data["matching_feats_bchw"], src_data["matching_feats_bkchw"]
@@ -149,7 +201,6 @@ class DepthModelCVHint(nn.Module):
             prior_feats = list(self.encoder(cur_data["image_b3hw"]))
             mcur, msrc = self.compute_matching_feats(cur_data["image_b3hw"], src_data["image_b3hw"],
                                                      unbatched_matching_encoder_forward)
-        dev = mcur.device
         src_K = src_data[f"K_s{ms}_b44"]
         cur_invK = cur_data[f"invK_s{ms}_b44"]
         ext, pose = self._relative_poses(cur_data, src_data, dev)
@@ -158,6 +209,8 @@ class DepthModelCVHint(nn.Module):
         max_depth = torch.tensor(self.run_opts.max_matching_depth).view(1, 1, 1, 1)
         cv = self._run_cost_volume(mcur, msrc, ext, pose, src_K, cur_invK, min_depth, max_depth, cur_data, return_mask)
 
+        if ev_late is not None:
+            torch.cuda.current_stream(dev).wait_event(ev_late)
         plan = self._network_plan(cv["volume"].shape, prior_feats)
         plan.load_inputs({"cv": cv["volume"], **{f"prior{i}": f for i, f in enumerate(prior_feats)}})
         plan.run()

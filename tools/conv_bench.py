@@ -36,13 +36,18 @@ def main():
     ap.add_argument("--math", default="tc3x")
     ap.add_argument("--only", default=None)
     ap.add_argument("--reps", type=int, default=20)
-    ap.add_argument("--debug", type=int, default=0)
+    ap.add_argument("--debug", default="0", help="comma-separated dtb200_debug_set values, one pass per value")
     args = ap.parse_args()
     dev = torch.device("cuda")
     torch.zeros(1, device=dev)
-    if args.debug:
-        L.check(L.lib().dtb200_debug_set(args.debug))
-        print("debug flags", args.debug)
+    for flags in [int(x) for x in args.debug.split(",")]:
+        L.check(L.lib().dtb200_debug_set(flags))
+        if flags:
+            print("debug flags", flags)
+        run(args, dev)
+
+
+def run(args, dev):
     torch.manual_seed(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     total_ms = 0.0
