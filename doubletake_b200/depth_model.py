@@ -124,6 +124,11 @@ class DepthModelCVHint(nn.Module):
         if not any(on_host(x) for d in trees for v in d.values() for x in (v if isinstance(v, (list, tuple)) else [v])):
             return cur_data, src_data, (None, None)
         main = torch.cuda.current_stream(dev)
+        # bound the host's run-ahead to two frames: staged inputs are recycled by the caching allocator instead of growing
+        # with every queued frame (a cudaMalloc inside the loop costs more than the copy it serves)
+        inflight = self.__dict__.setdefault("_inflight", [])
+        while len(inflight) >= 2:
+            inflight.pop(0).synchronize()
         copy = self.__dict__.get("_copy_stream")
         if copy is None or copy.device != dev:
             copy = self.__dict__["_copy_stream"] = torch.cuda.Stream(dev)
@@ -221,6 +226,8 @@ class DepthModelCVHint(nn.Module):
             lin = torch.empty_like(log_depth)
             L.check(L.lib().dtb200_exp(L.ptr(log_depth), L.ptr(lin), log_depth.numel(), L.stream()))
             depth_outputs[k.replace("log_", "")] = lin  # doubletake_model.py:410-418 (incl. the feature_s* quirk)
+        if ev_late is not None:
+            self.__dict__["_inflight"].append(torch.cuda.current_stream(dev).record_event())
         depth_outputs["lowest_cost_bhw"] = cv["lowest_cost"]
         depth_outputs["overall_mask_bhw"] = cv["mask"]
         return depth_outputs
