@@ -101,9 +101,13 @@ def model_weights(model, seed=2024):
 # clocks
 # --------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """nvidia-smi polled every 20 ms in a child process.  It is started BEFORE the warm-up (the tool needs a few hundred
+    ms to come up, longer than a short timed region) and every line carries nvidia-smi's own timestamp, so ``stop`` keeps
+    exactly the samples taken between the wall-clock marks of the timed regions."""
+
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -120,7 +124,19 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(stamp):
+        # "2026/10/17 01:48:12.345" (local time of the box, like time.time() through mktime)
+        try:
+            main, _, ms = stamp.partition(".")
+            return time.mktime(time.strptime(main, "%Y/%m/%d %H:%M:%S")) + (float("0." + ms) if ms else 0.0)
+        except Exception:
+            return None
+
+    def stop(self, windows=()):
+        """``windows``: (t0, t1) pairs of time.time() marks; samples outside every window are dropped (with a 50 ms
+        margin).  If no sample falls inside a window (a region shorter than the polling period) all samples are kept
+        and ``window`` says so."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -129,27 +145,29 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         try:
             for line in open(self.path):
                 parts = [p.strip() for p in line.split(",")]
-                if len(parts) < 9:
+                if len(parts) < 10:
                     continue
                 try:
-                    sm.append(float(parts[1]))
-                    mx.append(float(parts[2]))
+                    sm, mx = float(parts[2]), float(parts[3])
                 except ValueError:
                     continue
-                for n, v in zip(names, parts[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                rows.append((self._epoch(parts[0]), sm, mx,
+                             {n for n, v in zip(names, parts[6:10]) if v.lower().startswith("active")}))
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if r[0] is not None and any(t0 - 0.05 <= r[0] <= t1 + 0.05 for t0, t1 in windows)]
+        out["window"] = "timed regions" if inside else "whole run (no sample fell inside the timed regions)"
+        use = inside or rows
+        if use:
+            sm = sorted(r[1] for r in use)
+            reasons = set().union(*[r[3] for r in use])
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(r[2] for r in use), reasons=sorted(reasons), samples=len(use))
         return out
 
 
@@ -171,6 +189,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its banner there)
         dist.init_process_group("nccl", device_id=dev)
     torch.set_grad_enabled(False)
 
@@ -226,6 +246,10 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # before the warm-up: nvidia-smi takes longer to come up than a short timed region lasts
+
     # ---- warm-up (compiles the conv plan, packs weights)
     for i in range(max(args.warmup, 3)):
         step_resident(i)
@@ -233,14 +257,12 @@ def run_b200(args):
     barrier()
 
     # ---- device-timed region: one event pair per step, L2 flushed between steps outside the timed intervals
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = L.launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
+    w_timed0 = time.time()
     for i in range(args.steps):
         flush.zero_()
         starts[i].record()
@@ -248,18 +270,20 @@ def run_b200(args):
         ends[i].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    w_timed1 = time.time()
     launches = L.launch_count() - launches0
     dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
     dev_ms = reduce_max(dev_ms)
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end region: host buffers -> public API -> host result, wall clock between device syncs
     barrier()
     t0 = time.perf_counter()
+    w_e2e0 = time.time()
     for i in range(args.steps):
         step_e2e(i)
     barrier()
     e2e_s = reduce_max(time.perf_counter() - t0)
+    clocks = sampler.stop([(w_timed0, w_timed1), (w_e2e0, time.time())]) if rank == 0 else None
 
     # ---- per-kernel timing for the roofline (rank 0, N=1 semantics): cost-volume kernel and the conv plan, alone
     roof = None

@@ -49,8 +49,14 @@ def gather_depth_maps(local_depth: torch.Tensor, num_frames: int, group=None):
     recv = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
     dist.all_gather_into_tensor(recv.view(-1, *send.shape[1:]), send, group=group) if send.is_cuda else \
         dist.all_gather(list(recv.unbind(0)), send, group=group)
+    # recv[r, j] is global frame j * world + r (round-robin).  Even shards: a transpose is the frame order (a free view
+    # when every rank owns one frame); ragged shards: strided slice assignments -- no index tensors, so no host->device
+    # copies or syncs ride on the collective.
+    if per * world == num_frames:
+        return recv.transpose(0, 1).reshape((num_frames,) + tuple(local_depth.shape[1:]))
     out = local_depth.new_empty((num_frames,) + tuple(local_depth.shape[1:]))
     for r in range(world):
-        idx = shard_frames(num_frames, r, world)
-        out[idx] = recv[r, : len(idx)]
+        n = len(range(r, num_frames, world))
+        if n:
+            out[r::world] = recv[r, :n]
     return out
