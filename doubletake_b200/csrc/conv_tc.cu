@@ -422,6 +422,257 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
   }
 }
 
+// ======================================================================================================================
+// Halo-tile variant for 3x3 / stride-1 layers (the bulk of the decoder's time at 240x320 and 120x160).
+//
+// The tap-major kernel above re-reads every activation 9 times from L2 (one TMA box + one split per tap) and its 48 KB
+// stages leave room for only 4 K blocks in flight.  Here the A side of a stage is ONE patch of
+// (TH+2) x (TW+2) = 18 x 10 pixels x 32 channels (22.5 KB raw + 22.5 KB small), loaded by one TMA box and split once; the 9
+// taps read it through shared-memory descriptors that are only SHIFTED by whole pixels: tile row r = (ty, tx) of tap
+// (ky, kx) is patch pixel (ty + ky) * 10 + tx + kx, i.e. start address + (ky * 10 + kx) * 128 B with the 8-row core-matrix
+// stride (SBO) = one patch row = 1280 B.  tcgen05 applies SWIZZLE_128B on absolute shared-memory address bits, so a
+// shifted start needs no base_offset (measured: tools/halo_probe.cu, profiles/r01d_halo_probe.txt).  Weight tiles (one per
+// tap and chunk, the packed layout is unchanged) stream through their own ring.  Per 32-channel chunk: 1 TMA box + 1 split
+// + 9 weight tiles + 72 MMAs, instead of 9 boxes + 9 splits.
+constexpr int kHaloTW = 8, kHaloTH = 16;                       // 128 output pixels, 8 wide: one core-matrix group per tile row
+constexpr int kHaloPW = kHaloTW + 2, kHaloPH = kHaloTH + 2;    // patch
+constexpr int kHaloPatchBytes = kHaloPW * kHaloPH * 128;       // 23040 = the TMA box
+constexpr int kHaloSlotBytes = (kHaloPatchBytes + 1023) / 1024 * 1024;  // 23552: slots stay 1024-byte aligned
+constexpr int kHaloAStageBytes = 2 * kHaloSlotBytes;           // raw | small
+constexpr int kHaloAStages = 2;
+template <int BN>
+struct HaloCfg {
+  static constexpr int kBBytes = 2 * BN * 128;                 // B_big | B_small of one (tap, chunk)
+  static constexpr int kBStages = BN <= 64 ? 6 : 4;
+  static constexpr int kAccCols = 2 * BN;                      // merged accumulator (see kMerged above)
+  static constexpr int kTmemCols = 2 * kAccCols;
+  static constexpr int kSmemBytes = kHaloAStages * kHaloAStageBytes + kBStages * kBBytes + 1024 /*align*/ + 512 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const dtb200_conv_params p, const __grid_constant__ TcMaps maps,
+                                                                   KLayout kl, TcWork wk) {
+  using Cfg = HaloCfg<BN>;
+  constexpr int SA = kHaloAStages, SB = Cfg::kBStages;
+  static_assert(Cfg::kTmemCols <= 512, "accumulators exceed TMEM");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring_a = smem;                                   // SA x [raw patch | small patch]
+  uint8_t* ring_b = ring_a + SA * kHaloAStageBytes;         // SB x [B_big | B_small]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_b + SB * Cfg::kBBytes);
+  uint64_t* raw_full = bars;            // [SA] TMA box landed (1 arrival + tx)          A loader  -> splitters
+  uint64_t* a_full = raw_full + SA;     // [SA] small patch written (4 warps)             splitters -> MMA
+  uint64_t* a_empty = a_full + SA;      // [SA] tcgen05.commit after the 9th tap          MMA       -> A loader
+  uint64_t* b_full = a_empty + SA;      // [SB] weight tile landed (1 arrival + tx)       B loader  -> MMA
+  uint64_t* b_empty = b_full + SB;      // [SB] tcgen05.commit after the tap              MMA       -> B loader
+  uint64_t* acc_full = b_empty + SB;    // [2]
+  uint64_t* acc_empty = acc_full + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < SA; ++s) mbar_init(&raw_full[s], 1), mbar_init(&a_full[s], kSplitWarps), mbar_init(&a_empty[s], 1);
+    for (int s = 0; s < SB; ++s) mbar_init(&b_full[s], 1), mbar_init(&b_empty[s], 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&acc_full[s], 1), mbar_init(&acc_empty[s], kEpilogueWarps);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int chunks = kl.kb_per_tap;     // 32-channel chunks of the concatenated sources = A stages per item
+
+  auto decode = [&](long long item, int& bb, int& y0, int& x0, int& n_tile) {
+    n_tile = (int)(item % wk.n_tiles);
+    const int m_tile = (int)(item / wk.n_tiles);
+    const int per_img = wk.tiles_x * wk.tiles_y;
+    bb = m_tile / per_img;
+    const int t = m_tile - bb * per_img;
+    y0 = (t / wk.tiles_x) * kHaloTH;
+    x0 = (t % wk.tiles_x) * kHaloTW;
+  };
+
+  if (warp < kEpilogueWarps) {
+    // ============================================================ epilogue (as in conv_tc_kernel, merged accumulator)
+    const int row = warp * 32 + lane;
+    const int ty = row / kHaloTW, tx = row - ty * kHaloTW;
+    int use = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
+      int bb, y0, x0, n_tile;
+      decode(item, bb, y0, x0, n_tile);
+      const int buf = use & 1;
+      const int oy = y0 + ty, ox = x0 + tx;
+      const bool live = oy < p.out_h && ox < p.out_w;
+      const long long m = ((long long)bb * p.out_h + oy) * p.out_w + ox;
+      const int n_base = n_tile * BN;
+      float* dst = p.dst + m * p.out_c + n_base;
+      const float* res = p.residual ? p.residual + m * p.out_c + n_base : nullptr;
+      mbar_wait(&acc_full[buf], (use >> 1) & 1, 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * Cfg::kAccCols) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        float r[32];
+        const bool use_res = res != nullptr && live;
+        if (use_res) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) ldg256(res + cc + j, r + j);
+        }
+        float v[32], v2[32];
+        tmem_ld32(taddr + (uint32_t)cc, v);
+        tmem_ld32(taddr + (uint32_t)(BN + cc), v2);  // + A_big x B_small^T, accumulated in the upper half
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        if (!live) continue;
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = ld4(p.bias + n_base + cc + j);
+            v[j] += bv.x, v[j + 1] += bv.y, v[j + 2] += bv.z, v[j + 3] += bv.w;
+          }
+        }
+        if (use_res) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += r[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.act, p.act_slope);
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) stg256(dst + cc + j, v + j);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  } else if (warp < kMmaWarp) {
+    // ============================================================ splitters: small patch = x - tf32(x), same layout as raw
+    // (elementwise on 16-byte units, so the swizzle never has to be computed); all four warps share every patch
+    const int st = tid - kEpilogueWarps * 32;  // 0..127
+    constexpr int kUnits = kHaloPatchBytes / 16;  // 1440
+    const uint32_t ring_u = smem_u32(ring_a);
+    int stage = 0, phase = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
+#pragma unroll 1
+      for (int ch = 0; ch < chunks; ++ch) {
+        mbar_wait(&raw_full[stage], phase, 2);
+        const uint32_t raw_u = ring_u + (uint32_t)(stage * kHaloAStageBytes);
+        float4 v[12];
+#pragma unroll
+        for (int it = 0; it < 12; ++it) {
+          const int u = st + it * 128;
+          if (u < kUnits) v[it] = lds128(raw_u + (uint32_t)u * 16u);
+        }
+#pragma unroll
+        for (int it = 0; it < 12; ++it) {
+          const int u = st + it * 128;
+          if (u < kUnits) {
+            const float4 x = v[it];
+            const float4 big = make_float4(tf32_big(x.x), tf32_big(x.y), tf32_big(x.z), tf32_big(x.w));
+            sts128(raw_u + kHaloSlotBytes + (uint32_t)u * 16u, make_float4(x.x - big.x, x.y - big.y, x.z - big.z, x.w - big.w));
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[stage]);
+        if (++stage == SA) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ============================================================ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+    constexpr uint32_t idesc2 = umma_idesc_tf32(kBM, 2 * BN);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    // A: SBO = one patch row (10 pixels = 1280 B); B: SBO = 1024 B.  High words are constant, low words move by plain adds.
+    constexpr uint32_t kDescHiA = (uint32_t)(kHaloPW * 128 / 16) | (1u << 14) | (2u << 29);
+    constexpr uint32_t kDescHiB = 64u | (1u << 14) | (2u << 29);
+    const uint32_t lo_ring_a = ((smem_u32(ring_a) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t lo_ring_b = ((smem_u32(ring_b) & 0x3FFFFu) >> 4) | (1u << 16);
+    auto desc_a = [](uint32_t lo) { return ((uint64_t)kDescHiA << 32) | lo; };
+    auto desc_b = [](uint32_t lo) { return ((uint64_t)kDescHiB << 32) | lo; };
+    int sa = 0, pa = 0, sb = 0, pb = 0, use = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
+      const int buf = use & 1;
+      mbar_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1, 3);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_u + (uint32_t)(buf * Cfg::kAccCols);
+      for (int ch = 0; ch < chunks; ++ch) {
+        mbar_wait(&a_full[sa], pa, 4);                      // raw patch landed and small patch written
+        tc_fence_after();
+        const uint32_t lo_raw = lo_ring_a + (uint32_t)sa * (kHaloAStageBytes >> 4);
+        const uint32_t lo_small = lo_raw + (kHaloSlotBytes >> 4);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_full[sb], pb, 5);
+          tc_fence_after();
+          const int ky = tap / 3, kx = tap - ky * 3;
+          const uint32_t shift = (uint32_t)(ky * kHaloPW + kx) * (128u >> 4);  // whole pixels, in 16-byte units
+          const uint32_t lo_b_big = lo_ring_b + (uint32_t)sb * (Cfg::kBBytes >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t ko = ks * 2;  // 8 tf32 = 32 bytes along K inside the swizzled row
+              umma_tf32(tmem_d, desc_a(lo_raw + shift + ko), desc_b(lo_b_big + ko), idesc2, (ch | tap | ks) != 0);  // [big x big | big x small]
+              umma_tf32(tmem_d, desc_a(lo_small + shift + ko), desc_b(lo_b_big + ko), idesc, true);                 // small x big
+            }
+            umma_commit(&b_empty[sb]);
+            if (tap == 8) umma_commit(&a_empty[sa]);
+          }
+          __syncwarp();
+          if (++sb == SB) sb = 0, pb ^= 1;
+        }
+        if (++sa == SA) sa = 0, pa ^= 1;
+      }
+      if (elect_one()) umma_commit(&acc_full[buf]);
+      __syncwarp();
+    }
+  } else if (warp == kLoadWarp) {
+    // ============================================================ A loader: one TMA box (patch) per 32-channel chunk
+    int stage = 0, phase = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
+      int bb, y0, x0, n_tile;
+      decode(item, bb, y0, x0, n_tile);
+      int src = 0, c0 = 0;
+      for (int ch = 0; ch < chunks; ++ch) {
+        mbar_wait(&a_empty[stage], phase ^ 1, 6);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&raw_full[stage], kHaloPatchBytes);
+          tma_load_4d(ring_a + stage * kHaloAStageBytes, &maps.m[src], c0, x0 - 1, y0 - 1, bb, &raw_full[stage]);
+        }
+        __syncwarp();
+        if (++stage == SA) stage = 0, phase ^= 1;
+        c0 += kBK;
+        if (c0 >= (src == 0 ? kl.src_c[0] : (src == 1 ? kl.src_c[1] : kl.src_c[2]))) c0 = 0, ++src;
+      }
+    }
+  } else {
+    // ============================================================ B loader: weight tile of (tap, chunk), packed tap-major
+    int stage = 0, phase = 0;
+    for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
+      int bb, y0, x0, n_tile;
+      decode(item, bb, y0, x0, n_tile);
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) + (size_t)n_tile * wk.num_kb_total * Cfg::kBBytes;
+      for (int ch = 0; ch < chunks; ++ch) {
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_empty[stage], phase ^ 1, 7);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&b_full[stage], Cfg::kBBytes);
+            bulk_g2s(ring_b + stage * Cfg::kBBytes, wbase + (size_t)(tap * chunks + ch) * Cfg::kBBytes, Cfg::kBBytes, &b_full[stage]);
+          }
+          __syncwarp();
+          if (++stage == SB) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
 // OIHW (out_c, in_c, k, k) -> per (N tile, K block): [B_big tile | B_small tile], each [BN rows][32 fp32] in the
 // SWIZZLE_128B K-major shared-memory image; K blocks follow KLayout (tap-major, per source 32-channel chunks, zero padded).
 __global__ void pack_weight_tc_kernel(const float* __restrict__ oihw, float* __restrict__ packed, int out_c, int in_c,
@@ -514,6 +765,7 @@ void conv_tc_init() {
   cudaFuncSetAttribute(conv_tc_kernel<64, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true, 2>::kSmemBytes);
   cudaFuncSetAttribute(conv_tc_kernel<64, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true, 3>::kSmemBytes);
   cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true>::kSmemBytes);
+  cudaFuncSetAttribute(conv_tc_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64>::kSmemBytes);
   cudaGetLastError();
   done = true;
 }
@@ -650,6 +902,36 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
   wk.n_tiles = p.out_c / bn;
   wk.total = (long long)wk.m_tiles * wk.n_tiles * wk.splits;
   const int zsplits = wk.splits;
+
+  // 3x3 / stride-1 layers with at least one full round of 8 x 16 tiles: halo-tile kernel (one patch load + one split per
+  // 9 taps).  Development switch: bit 7 of the flags turns it on.
+  if ((conv_flags() & 128) && p.ksize == 3 && p.stride == 1 && bn == 64 && splits == 1 && p.in_h == p.out_h && p.in_w == p.out_w) {
+    TcWork hw = wk;
+    hw.tw = kHaloTW, hw.th = kHaloTH;
+    hw.tiles_x = (p.out_w + kHaloTW - 1) / kHaloTW;
+    hw.tiles_y = (p.out_h + kHaloTH - 1) / kHaloTH;
+    hw.m_tiles = p.batch * hw.tiles_x * hw.tiles_y;
+    hw.total = (long long)hw.m_tiles * hw.n_tiles;
+    if (hw.total >= 148) {
+      TcMaps hmaps;
+      memset(&hmaps, 0, sizeof(hmaps));
+      for (int s = 0; s < p.num_src; ++s) {
+        const cuuint64_t C = (cuuint64_t)p.src_c[s];
+        cuuint64_t dims[4] = {C, (cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.batch};
+        cuuint64_t strides[3] = {C * 4, (cuuint64_t)p.in_w * C * 4, (cuuint64_t)p.in_h * p.in_w * C * 4};
+        cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)kHaloPW, (cuuint32_t)kHaloPH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&hmaps.m[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.src[s]), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(DTB200_ERR_CUDA, "conv (tc3x halo): cuTensorMapEncodeTiled failed with code %s%lld", "", (long long)r);
+      }
+      conv_tc_init();
+      const unsigned hgrid = (unsigned)(hw.total < g_num_sms ? hw.total : g_num_sms);
+      conv_tc_halo_kernel<64><<<hgrid, kThreads, HaloCfg<64>::kSmemBytes, stream>>>(p, hmaps, kl, hw);
+      return check_launch("conv_tc_halo_kernel");
+    }
+  }
 
   // one 4-D tensor map (C, W, H, B) per source: box = 32 channels x (tw x th) output pixels; for stride 2 the box spans
   // 2*tw x 2*th input pixels of which every second one is written (elementStrides)
