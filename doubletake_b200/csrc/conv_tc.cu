@@ -49,6 +49,8 @@ struct TcCfg {
 //   bit 0: issue the 64-channel tiles as three N=64 MMAs per K step instead of the merged N=128 + N=64 pair
 //   bit 1: same for the 128-channel tiles (their merged form, N=256 + N=128, takes all 512 TMEM columns)
 //   bit 2: previous split-K rule (many short items) instead of the round-count cost model
+//   bit 7: no halo-tile kernel (3x3 / stride-1 layers use the tap-major kernel too); bit 3: halo kernel with 3 taps per
+//          weight-ring stage
 //   bits 8..12: timing knock-outs of the tensor-core conv pipeline (results are WRONG; tools/conv_bench.py --debug)
 static int g_flags = -1;
 static int conv_flags() {
@@ -440,26 +442,30 @@ constexpr int kHaloPatchBytes = kHaloPW * kHaloPH * 128;       // 23040 = the TM
 constexpr int kHaloSlotBytes = (kHaloPatchBytes + 1023) / 1024 * 1024;  // 23552: slots stay 1024-byte aligned
 constexpr int kHaloAStageBytes = 2 * kHaloSlotBytes;           // raw | small
 constexpr int kHaloAStages = 2;
-template <int BN>
+// kTB = taps per weight-ring stage: the issuing thread pays one mbarrier wait (~190 clk, never hidden: MMA issue is
+// synchronous with the tensor pipe, tools/umma_bench.cu) and one commit per stage, so kTB = 3 amortises them over 24 MMAs.
+template <int BN, int kTB = 1>
 struct HaloCfg {
   static constexpr int kBBytes = 2 * BN * 128;                 // B_big | B_small of one (tap, chunk)
-  static constexpr int kBStages = BN <= 64 ? 6 : 4;
+  static constexpr int kBStageBytes = kTB * kBBytes;
+  static constexpr int kBStages = kTB == 1 ? (BN <= 64 ? 6 : 4) : 2;
   static constexpr int kAccCols = 2 * BN;                      // merged accumulator (see kMerged above)
   static constexpr int kTmemCols = 2 * kAccCols;
-  static constexpr int kSmemBytes = kHaloAStages * kHaloAStageBytes + kBStages * kBBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int kSmemBytes = kHaloAStages * kHaloAStageBytes + kBStages * kBStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, int kTB>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const dtb200_conv_params p, const __grid_constant__ TcMaps maps,
                                                                    KLayout kl, TcWork wk) {
-  using Cfg = HaloCfg<BN>;
+  using Cfg = HaloCfg<BN, kTB>;
   constexpr int SA = kHaloAStages, SB = Cfg::kBStages;
   static_assert(Cfg::kTmemCols <= 512, "accumulators exceed TMEM");
+  static_assert(9 % kTB == 0, "a weight-ring stage holds a whole number of tap groups");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring_a = smem;                                   // SA x [raw patch | small patch]
-  uint8_t* ring_b = ring_a + SA * kHaloAStageBytes;         // SB x [B_big | B_small]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_b + SB * Cfg::kBBytes);
+  uint8_t* ring_b = ring_a + SA * kHaloAStageBytes;         // SB x kTB x [B_big | B_small]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_b + SB * Cfg::kBStageBytes);
   uint64_t* raw_full = bars;            // [SA] TMA box landed (1 arrival + tx)          A loader  -> splitters
   uint64_t* a_full = raw_full + SA;     // [SA] small patch written (4 warps)             splitters -> MMA
   uint64_t* a_empty = a_full + SA;      // [SA] tcgen05.commit after the 9th tap          MMA       -> A loader
@@ -602,21 +608,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const dtb200_
         const uint32_t lo_raw = lo_ring_a + (uint32_t)sa * (kHaloAStageBytes >> 4);
         const uint32_t lo_small = lo_raw + (kHaloSlotBytes >> 4);
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int g = 0; g < 9 / kTB; ++g) {
           mbar_wait(&b_full[sb], pb, 5);
           tc_fence_after();
-          const int ky = tap / 3, kx = tap - ky * 3;
-          const uint32_t shift = (uint32_t)(ky * kHaloPW + kx) * (128u >> 4);  // whole pixels, in 16-byte units
-          const uint32_t lo_b_big = lo_ring_b + (uint32_t)sb * (Cfg::kBBytes >> 4);
+          const uint32_t lo_b_stage = lo_ring_b + (uint32_t)sb * (Cfg::kBStageBytes >> 4);
           if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t ko = ks * 2;  // 8 tf32 = 32 bytes along K inside the swizzled row
-              umma_tf32(tmem_d, desc_a(lo_raw + shift + ko), desc_b(lo_b_big + ko), idesc2, (ch | tap | ks) != 0);  // [big x big | big x small]
-              umma_tf32(tmem_d, desc_a(lo_small + shift + ko), desc_b(lo_b_big + ko), idesc, true);                 // small x big
+            for (int t = 0; t < kTB; ++t) {
+              const int tap = g * kTB + t;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              const uint32_t shift = (uint32_t)(ky * kHaloPW + kx) * (128u >> 4);  // whole pixels, in 16-byte units
+              const uint32_t lo_b_big = lo_b_stage + (uint32_t)t * (Cfg::kBBytes >> 4);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t ko = ks * 2;  // 8 tf32 = 32 bytes along K inside the swizzled row
+                umma_tf32(tmem_d, desc_a(lo_raw + shift + ko), desc_b(lo_b_big + ko), idesc2, (ch | tap | ks) != 0);  // [big x big | big x small]
+                umma_tf32(tmem_d, desc_a(lo_small + shift + ko), desc_b(lo_b_big + ko), idesc, true);                 // small x big
+              }
             }
             umma_commit(&b_empty[sb]);
-            if (tap == 8) umma_commit(&a_empty[sa]);
+            if (g == 9 / kTB - 1) umma_commit(&a_empty[sa]);
           }
           __syncwarp();
           if (++sb == SB) sb = 0, pb ^= 1;
@@ -653,11 +664,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const dtb200_
       decode(item, bb, y0, x0, n_tile);
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) + (size_t)n_tile * wk.num_kb_total * Cfg::kBBytes;
       for (int ch = 0; ch < chunks; ++ch) {
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int g = 0; g < 9 / kTB; ++g) {
           mbar_wait(&b_empty[stage], phase ^ 1, 7);
           if (elect_one()) {
-            mbar_arrive_expect_tx(&b_full[stage], Cfg::kBBytes);
-            bulk_g2s(ring_b + stage * Cfg::kBBytes, wbase + (size_t)(tap * chunks + ch) * Cfg::kBBytes, Cfg::kBBytes, &b_full[stage]);
+            mbar_arrive_expect_tx(&b_full[stage], Cfg::kBStageBytes);
+#pragma unroll
+            for (int t = 0; t < kTB; ++t)
+              bulk_g2s(ring_b + stage * Cfg::kBStageBytes + t * Cfg::kBBytes,
+                       wbase + (size_t)((g * kTB + t) * chunks + ch) * Cfg::kBBytes, Cfg::kBBytes, &b_full[stage]);
           }
           __syncwarp();
           if (++stage == SB) stage = 0, phase ^= 1;
@@ -765,7 +779,8 @@ void conv_tc_init() {
   cudaFuncSetAttribute(conv_tc_kernel<64, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true, 2>::kSmemBytes);
   cudaFuncSetAttribute(conv_tc_kernel<64, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true, 3>::kSmemBytes);
   cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true>::kSmemBytes);
-  cudaFuncSetAttribute(conv_tc_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64>::kSmemBytes);
+  cudaFuncSetAttribute(conv_tc_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64, 1>::kSmemBytes);
+  cudaFuncSetAttribute(conv_tc_halo_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64, 3>::kSmemBytes);
   cudaGetLastError();
   done = true;
 }
@@ -904,8 +919,9 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
   const int zsplits = wk.splits;
 
   // 3x3 / stride-1 layers with at least one full round of 8 x 16 tiles: halo-tile kernel (one patch load + one split per
-  // 9 taps).  Development switch: bit 7 of the flags turns it on.
-  if ((conv_flags() & 128) && p.ksize == 3 && p.stride == 1 && bn == 64 && splits == 1 && p.in_h == p.out_h && p.in_w == p.out_w) {
+  // 9 taps).  Development switches: bit 7 of the flags turns it OFF (tap-major kernel everywhere), bit 3 selects the
+  // 3-taps-per-weight-stage variant.
+  if (!(conv_flags() & 128) && p.ksize == 3 && p.stride == 1 && bn == 64 && splits == 1 && p.in_h == p.out_h && p.in_w == p.out_w) {
     TcWork hw = wk;
     hw.tw = kHaloTW, hw.th = kHaloTH;
     hw.tiles_x = (p.out_w + kHaloTW - 1) / kHaloTW;
@@ -928,7 +944,10 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
       }
       conv_tc_init();
       const unsigned hgrid = (unsigned)(hw.total < g_num_sms ? hw.total : g_num_sms);
-      conv_tc_halo_kernel<64><<<hgrid, kThreads, HaloCfg<64>::kSmemBytes, stream>>>(p, hmaps, kl, hw);
+      if (conv_flags() & 8)
+        conv_tc_halo_kernel<64, 3><<<hgrid, kThreads, HaloCfg<64, 3>::kSmemBytes, stream>>>(p, hmaps, kl, hw);
+      else
+        conv_tc_halo_kernel<64, 1><<<hgrid, kThreads, HaloCfg<64, 1>::kSmemBytes, stream>>>(p, hmaps, kl, hw);
       return check_launch("conv_tc_halo_kernel");
     }
   }
