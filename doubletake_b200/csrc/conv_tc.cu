@@ -49,8 +49,8 @@ struct TcCfg {
 //   bit 0: issue the 64-channel tiles as three N=64 MMAs per K step instead of the merged N=128 + N=64 pair
 //   bit 1: same for the 128-channel tiles (their merged form, N=256 + N=128, takes all 512 TMEM columns)
 //   bit 2: previous split-K rule (many short items) instead of the round-count cost model
-//   bit 7: no halo-tile kernel (3x3 / stride-1 layers use the tap-major kernel too); bit 3: halo kernel with 3 taps per
-//          weight-ring stage
+//   bit 7: no halo-tile kernel (3x3 / stride-1 layers use the tap-major kernel too); bit 3: halo kernel with 1 tap per
+//          weight-ring stage instead of 3
 //   bits 8..12: timing knock-outs of the tensor-core conv pipeline (results are WRONG; tools/conv_bench.py --debug)
 static int g_flags = -1;
 static int conv_flags() {
@@ -920,7 +920,7 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
 
   // 3x3 / stride-1 layers with at least one full round of 8 x 16 tiles: halo-tile kernel (one patch load + one split per
   // 9 taps).  Development switches: bit 7 of the flags turns it OFF (tap-major kernel everywhere), bit 3 selects the
-  // 3-taps-per-weight-stage variant.
+  // one-tap-per-weight-stage variant (default: 3 taps per stage).
   if (!(conv_flags() & 128) && p.ksize == 3 && p.stride == 1 && bn == 64 && splits == 1 && p.in_h == p.out_h && p.in_w == p.out_w) {
     TcWork hw = wk;
     hw.tw = kHaloTW, hw.th = kHaloTH;
@@ -944,10 +944,10 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
       }
       conv_tc_init();
       const unsigned hgrid = (unsigned)(hw.total < g_num_sms ? hw.total : g_num_sms);
-      if (conv_flags() & 8)
-        conv_tc_halo_kernel<64, 3><<<hgrid, kThreads, HaloCfg<64, 3>::kSmemBytes, stream>>>(p, hmaps, kl, hw);
-      else
+      if (conv_flags() & 8)  // one tap per weight-ring stage (6 stages): 51.2 us on the 240x320 64->64 layer vs 45.1 us
         conv_tc_halo_kernel<64, 1><<<hgrid, kThreads, HaloCfg<64, 1>::kSmemBytes, stream>>>(p, hmaps, kl, hw);
+      else
+        conv_tc_halo_kernel<64, 3><<<hgrid, kThreads, HaloCfg<64, 3>::kSmemBytes, stream>>>(p, hmaps, kl, hw);
       return check_launch("conv_tc_halo_kernel");
     }
   }
