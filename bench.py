@@ -34,6 +34,8 @@ METRIC = "depth frames/sec at 640x480x64planes x7views"
 UNIT = "frames/s"
 WORKLOAD = "cfg2"
 L2_FLUSH_BYTES = 256 << 20
+WORKLOAD_DESC = ("cfg2: DoubleTake 640x480 image, 120x160x16 matching feats, 64 planes, 7 src views, "
+                 "rendered-depth hint on, batch 1 per GPU, CVEncoder+DepthDecoderPP (effnetv2-s priors)")
 
 
 def measured_peaks():
@@ -302,9 +304,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.math == "exact" else "f32 via 3xTF32 (tf32 big/small split, fp32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": "cfg2: DoubleTake 640x480 image, 120x160x16 matching feats, 64 planes, 7 src views, "
-                                   "rendered-depth hint on, batch 1 per GPU, CVEncoder+DepthDecoderPP (effnetv2-s priors)",
-                       "math": args.math, "frames_per_step": frames_per_step,
+            "config": {"workload": WORKLOAD_DESC, "math": args.math, "frames_per_step": frames_per_step,
                        "l2": "256 MiB L2 flush between timed steps (outside the per-step event pairs); 4 rotating input sets",
                        "weights": "random-init (seeded), reference architecture",
                        "wall_ms_per_step_incl_flush": round(1e3 * t_wall / args.steps, 4)},
@@ -482,7 +482,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": round(1e3 * dt_s / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2 (CPU arm: reference algorithm, torch CPU ops, all host threads)", "sample": sample},
+        "config": {"workload": WORKLOAD_DESC, "math": "f32 (reference algorithm, torch CPU ops, host threads)",
+                   "sample": sample},
         "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
