@@ -52,6 +52,25 @@ class ConvParams(C.Structure):
     ]
 
 
+TSDF_MAX_FRAMES = 8
+TSDF_SEMANTICS = {"aten_cpu": 0, "aten_cuda": 1}
+
+
+class TsdfFrame(C.Structure):
+    _fields_ = [("depth", fp), ("mask", fp), ("P", C.c_float * 12), ("box_min", C.c_float * 3), ("box_max", C.c_float * 3)]
+
+
+class TsdfIntegrateParams(C.Structure):
+    _fields_ = [
+        ("values", fp), ("weights", fp), ("voxel_coords", fp),
+        ("origin", C.c_float * 3), ("voxel_size", C.c_float), ("dims", C.c_int32 * 3),
+        ("img_h", C.c_int32), ("img_w", C.c_int32), ("num_frames", C.c_int32), ("semantics", C.c_int32),
+        ("min_depth", C.c_float), ("depth_range", C.c_float), ("max_depth_h", C.c_float), ("truncation", C.c_float),
+        ("trunc_check_h", C.c_float),
+        ("frames", TsdfFrame * TSDF_MAX_FRAMES),
+    ]
+
+
 # every symbol include/doubletake_b200.h declares (tests/test_capi_symbols.py checks the header against this list)
 SYMBOLS = {
     "dtb200_abi_version": (C.c_int, []),
@@ -78,6 +97,8 @@ SYMBOLS = {
                                   + [C.c_int32]),
     "dtb200_relative_poses": (C.c_int, [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, fp]),
     "dtb200_exp": (C.c_int, [fp, fp, C.c_uint64, fp]),
+    "dtb200_tsdf_integrate": (C.c_int, [C.POINTER(TsdfIntegrateParams), fp]),
+    "dtb200_tsdf_sample": (C.c_int, [fp, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_float, fp, fp, C.c_int64, C.c_int32, fp]),
 }
 
 _lib = None

@@ -1,0 +1,219 @@
+"""B200 mirror of the reference's TSDF volume and depth fuser (reference ``tools/tsdf.py``) -- SURVEY.md §8f row N2, the
+hint-production step on the other side of the hot path: the predicted ``depth_pred_s0_b1hw`` is fused into a TSDF
+(``TSDFFuser.integrate_depth``, tools/tsdf.py:414-558) and the fused confidence is read back as ``sampled_weights_b1hw``
+for the next keyframe's hint (``TSDF.sample_tsdf``, :277-337; test_incremental.py:220-252).
+
+Same class names, constructor arguments, method signatures and ``.npz`` format as the reference.  The volume lives in HBM
+as the reference's fp16 tensors; ``integrate_depth`` is ONE CUDA kernel per batch of up to 8 frames
+(``csrc/tsdf.cu``), ``sample_tsdf`` one kernel.  No CPU fallback: ``use_gpu=False`` raises.
+Mesh extraction (``to_mesh*``, marching cubes) is row N3 and not part of this engine yet.
+
+Numerics: the kernels reproduce the reference's fp16 torch ops rounding for rounding.  fp16 ``grid_sample`` behaves
+differently in ATen's CPU and CUDA builds (index arithmetic precision, non-finite indices); ``semantics="aten_cpu"``
+(default) is what the golden fixtures pin (the reference executed on CPU), ``"aten_cuda"`` follows GridSampler.cuh.
+``sample_tsdf`` follows the reference's fp32 branch (its CUDA branch rounds the coordinates to fp16 first).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _matmul_h(a, b):
+    """fp16 @ fp16 -> fp16 as ATen's generic CPU gemm evaluates it (fp32 accumulation in k order, one rounding), spelled
+    out so the few 4x4 products below do not depend on which fp16 GEMM path the host CPU offers."""
+    a32, b32 = a.float(), b.float()
+    acc = torch.zeros(a32.shape[:-1] + b32.shape[-1:], dtype=torch.float32)
+    for k in range(a32.shape[-1]):
+        acc = acc + a32[..., :, k:k + 1] * b32[..., k:k + 1, :]
+    return acc.half()
+
+
+def get_frustum_bounds(invK_44, world_T_cam_44, min_depth=0.1, max_depth=10.0, img_h=480, img_w=640):
+    """reference tools/tsdf.py:15-50 on fp16 CPU matrices: world-space bounding box of the view frustum."""
+    corners = torch.tensor([[0, 0, 1, 1], [img_w, 0, 1, 1], [0, img_h, 1, 1], [img_w, img_h, 1, 1]],
+                           dtype=invK_44.dtype).T
+    pts = _matmul_h(invK_44, corners)
+    near, far = pts.clone(), pts.clone()
+    near[:3] *= min_depth
+    far[:3] *= max_depth
+    world = _matmul_h(world_T_cam_44, torch.cat((near, far), dim=1))
+    return world.amin(dim=1)[:3], world.amax(dim=1)[:3]
+
+
+class TSDF:
+    """reference ``TSDF`` (tools/tsdf.py:53-337): fp16 voxel grid, values, weights."""
+
+    VOX_MOD = 8  # volume dimensions are multiples of 8 (the kernels rely on it: one 16-byte vector per 8 voxels)
+
+    def __init__(self, voxel_coords_3hwd, tsdf_values, tsdf_weights, voxel_size, origin, _origin_f32=None):
+        self.voxel_coords_3hwd = None if voxel_coords_3hwd is None else voxel_coords_3hwd.half()
+        self.tsdf_values = tsdf_values.half()
+        self.tsdf_weights = tsdf_weights.half()
+        self.voxel_size = voxel_size
+        self.origin = origin.half()
+        # set by from_bounds: the grid is origin + index * voxel_size, so the kernel regenerates it in registers
+        self._origin_f32 = _origin_f32
+
+    @classmethod
+    def from_file(cls, tsdf_file):
+        data = np.load(tsdf_file)
+        return cls(torch.from_numpy(data["voxel_coords_3hwd"]), torch.from_numpy(data["tsdf_values"]),
+                   torch.from_numpy(data["tsdf_weights"]), data["voxel_size"].item(), torch.from_numpy(data["origin"]))
+
+    @classmethod
+    def from_mesh(cls, mesh, voxel_size):
+        """Bounds of ``mesh.vertices`` (any object with an (N,3) ``vertices`` array) plus 3 voxels (:102-121)."""
+        vmax, vmin = np.asarray(mesh.vertices).max(0), np.asarray(mesh.vertices).min(0)
+        bounds = {f"{a}min": vmin[i] - 3 * voxel_size for i, a in enumerate("xyz")}
+        bounds.update({f"{a}max": vmax[i] + 3 * voxel_size for i, a in enumerate("xyz")})
+        return cls.from_bounds(bounds, voxel_size)
+
+    @classmethod
+    def from_bounds(cls, bounds, voxel_size, lazy_grid=False):
+        """reference :122-151.  ``lazy_grid=True`` (extension) skips materialising the (3,X,Y,Z) coordinate grid -- the
+        kernels regenerate it bit-identically -- and allocates the volume directly in HBM: the reference's default
+        20 m cube at 4 cm is 128 M voxels, i.e. 768 MB of coordinates that are never read here."""
+        for key in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax"):
+            if key not in bounds:
+                raise KeyError("Provided bounds dict need to have keys'xmin', 'xmax', 'ymin', 'ymax', 'zmin', 'zmax'!")
+        dims = tuple(int(np.ceil((bounds[a + "max"] - bounds[a + "min"]) / voxel_size / cls.VOX_MOD)) * cls.VOX_MOD
+                     for a in "xyz")
+        origin = torch.FloatTensor([bounds["xmin"], bounds["ymin"], bounds["zmin"]])
+        if lazy_grid:
+            values = torch.full(dims, -1.0, dtype=torch.float16, device="cuda")
+            return cls(None, values, torch.zeros_like(values), voxel_size, origin, _origin_f32=origin.clone())
+        coords = cls.generate_voxel_coords(origin, dims, voxel_size).half()
+        return cls(coords, -torch.ones_like(coords[0]), torch.zeros_like(coords[0]), voxel_size, origin,
+                   _origin_f32=origin.clone())
+
+    @classmethod
+    def generate_voxel_coords(cls, origin, volume_dims, voxel_size):
+        grid = torch.meshgrid([torch.arange(vd) for vd in volume_dims], indexing="ij")
+        return origin.view(3, 1, 1, 1) + torch.stack(grid, 0) * voxel_size
+
+    def cuda(self):
+        if self.voxel_coords_3hwd is not None:
+            self.voxel_coords_3hwd = self.voxel_coords_3hwd.cuda()
+        self.tsdf_values = self.tsdf_values.cuda()
+        if self.tsdf_weights is not None:
+            self.tsdf_weights = self.tsdf_weights.cuda()
+
+    def cpu(self):
+        if self.voxel_coords_3hwd is not None:
+            self.voxel_coords_3hwd = self.voxel_coords_3hwd.cpu()
+        self.tsdf_values = self.tsdf_values.cpu()
+        if self.tsdf_weights is not None:
+            self.tsdf_weights = self.tsdf_weights.cpu()
+
+    def save_tsdf(self, filepath):
+        if self.voxel_coords_3hwd is None:  # lazy grid: materialise it for the file format
+            self.voxel_coords_3hwd = self.generate_voxel_coords(self._origin_f32, tuple(self.tsdf_values.shape),
+                                                                self.voxel_size).half()
+        np.savez_compressed(
+            filepath, tsdf_values=self.tsdf_values.cpu().numpy().astype(np.float16),
+            tsdf_weights=self.tsdf_weights.cpu().numpy().astype(np.float16),
+            origin=self.origin.cpu().numpy().astype(np.float16),
+            voxel_coords_3hwd=self.voxel_coords_3hwd.cpu().numpy().astype(np.float16), voxel_size=self.voxel_size)
+
+    def to_mesh(self, *a, **k):
+        raise NotImplementedError("mesh extraction (marching cubes) is SURVEY.md §8f row N3, not part of doubletake_b200 yet")
+
+    to_mesh_pytorch3d = save_mesh = to_mesh
+
+    def sample_tsdf(self, world_points_N3, what_to_sample="tsdf", sampling_method="bilinear"):
+        """(N,3) world points -> (N,) fp32 samples of the TSDF or the weights (tools/tsdf.py:277-337)."""
+        if not (world_points_N3.ndim == 2 and world_points_N3.shape[1] == 3):
+            raise ValueError("world_points_N3 must have shape (N, 3)! Instead got shape {}".format(world_points_N3.shape))
+        if what_to_sample not in ("tsdf", "weights"):
+            raise ValueError(f"what_to_sample must be 'tsdf' or 'weights', got {what_to_sample}")
+        modes = {"bilinear": 0, "trilinear": 0, "nearest": 1}
+        if sampling_method not in modes:
+            raise ValueError(f"unknown sampling_method {sampling_method}")
+        self.cuda()
+        volume = (self.tsdf_values if what_to_sample == "tsdf" else self.tsdf_weights).contiguous()
+        pts = L.f32(world_points_N3, volume.device)
+        out = torch.empty(pts.shape[0], dtype=torch.float32, device=volume.device)
+        dims = (C.c_int32 * 3)(*volume.shape)
+        origin_h = (C.c_float * 3)(*[float(v) for v in self.origin.float().cpu()])
+        L.check(L.lib().dtb200_tsdf_sample(L.ptr(volume), dims, origin_h, float(self.voxel_size), L.ptr(pts), L.ptr(out),
+                                           pts.shape[0], modes[sampling_method], L.stream()))
+        return out
+
+
+class TSDFFuser:
+    """reference ``TSDFFuser`` (tools/tsdf.py:340-558)."""
+
+    def __init__(self, tsdf, min_depth=0.5, max_depth=5.0, use_gpu=True, semantics="aten_cpu"):
+        if not use_gpu:
+            raise RuntimeError("doubletake_b200 runs on CUDA only (no CPU fallback): use_gpu must be True")
+        if semantics not in L.TSDF_SEMANTICS:
+            raise ValueError(f"semantics must be one of {sorted(L.TSDF_SEMANTICS)}")
+        self.tsdf = tsdf
+        self.min_depth = min_depth
+        self.max_depth = max_depth
+        self.use_gpu = use_gpu
+        self.semantics = semantics
+        self.truncation_size = 3.0
+        self.maxW = 100.0
+
+    voxel_coords_3hwd = property(lambda self: self.tsdf.voxel_coords_3hwd)
+    tsdf_values = property(lambda self: self.tsdf.tsdf_values)
+    tsdf_weights = property(lambda self: self.tsdf.tsdf_weights)
+    voxel_size = property(lambda self: self.tsdf.voxel_size)
+    shape = property(lambda self: self.tsdf.tsdf_values.shape)
+    truncation = property(lambda self: self.truncation_size * self.tsdf.voxel_size)
+
+    def _frame_constants(self, cam_T_world_44, K_44, img_h, img_w):
+        """Per-frame host constants with the reference's own small fp16 ops (tools/tsdf.py:444-450,398-407)."""
+        depth_max = self.max_depth + self.truncation + 0.1
+        invK = torch.inverse(K_44.float()).half()
+        world_T_cam = torch.inverse(cam_T_world_44.float()).half()
+        lo, hi = get_frustum_bounds(invK, world_T_cam, 0.01, depth_max, img_h, img_w)
+        P = _matmul_h(K_44, cam_T_world_44)[:3]
+        return P.float().flatten().tolist(), lo.float().tolist(), hi.float().tolist()
+
+    def integrate_depth(self, depth_b1hw, cam_T_world_T_b44, K_b44, depth_mask_b1hw=None, extended_neg_truncation=False):
+        """Integrates a batch of depth maps into the volume, in order (tools/tsdf.py:414-558)."""
+        self.tsdf.cuda()
+        values, weights = self.tsdf.tsdf_values, self.tsdf.tsdf_weights
+        if not (values.is_contiguous() and weights.is_contiguous()):
+            raise RuntimeError("TSDF volumes must be contiguous")
+        dev = values.device
+        depth = depth_b1hw.to(dev).half().contiguous()
+        mask = None if depth_mask_b1hw is None else depth_mask_b1hw.to(dev).to(torch.uint8).contiguous()
+        B, _, img_h, img_w = depth.shape
+        T_cpu, K_cpu = cam_T_world_T_b44.detach().cpu().half(), K_b44.detach().cpu().half()
+        p = L.TsdfIntegrateParams()
+        p.values, p.weights = L.ptr(values), L.ptr(weights)
+        if self.tsdf._origin_f32 is not None:
+            p.voxel_coords = None
+            p.origin = (C.c_float * 3)(*[float(v) for v in self.tsdf._origin_f32])
+        else:
+            p.voxel_coords = L.ptr(self.tsdf.voxel_coords_3hwd.contiguous())
+        p.voxel_size = float(self.voxel_size)
+        p.dims = (C.c_int32 * 3)(*values.shape)
+        p.img_h, p.img_w = img_h, img_w
+        p.semantics = L.TSDF_SEMANTICS[self.semantics]
+        p.min_depth = float(self.min_depth)
+        p.depth_range = float(self.max_depth - self.min_depth)
+        p.max_depth_h = float(torch.tensor(self.max_depth).half())
+        p.truncation = float(self.truncation)
+        p.trunc_check_h = float(torch.tensor(-self.truncation * (1.5 if extended_neg_truncation else 1.0)).half())
+        for s in range(0, B, L.TSDF_MAX_FRAMES):
+            n = min(L.TSDF_MAX_FRAMES, B - s)
+            p.num_frames = n
+            for i in range(n):
+                P, lo, hi = self._frame_constants(T_cpu[s + i], K_cpu[s + i], img_h, img_w)
+                fr = p.frames[i]
+                fr.depth = depth[s + i].data_ptr()
+                fr.mask = None if mask is None else mask[s + i].data_ptr()
+                fr.P = (C.c_float * 12)(*P)
+                fr.box_min = (C.c_float * 3)(*lo)
+                fr.box_max = (C.c_float * 3)(*hi)
+            L.check(L.lib().dtb200_tsdf_integrate(C.byref(p), L.stream()))
+        # `depth` / `mask` stay referenced until the launches are enqueued; the caching allocator keeps them valid on this stream

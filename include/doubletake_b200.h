@@ -203,6 +203,59 @@ int dtb200_relative_poses(const float* src_cam_T_world, const float* src_world_T
 /* out = exp(in), elementwise (experiment_modules/doubletake_model.py:410-418) */
 int dtb200_exp(const float* src, float* dst, uint64_t count, dtb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * TSDF fusion of predicted depth maps and sampling of the fused confidence: the hint-production step on the other side
+ * of the hot path.  Replaces reference tools/tsdf.py:
+ *   TSDFFuser.integrate_depth (:414-558)  -> dtb200_tsdf_integrate
+ *   TSDF.sample_tsdf          (:277-337)  -> dtb200_tsdf_sample
+ * The volume is the reference's: fp16 TSDF values and weights of shape (X, Y, Z), Z fastest, dims multiples of 8
+ * (TSDF.VOX_MOD); voxel (i,j,k) sits at fp16(origin + (i,j,k) * voxel_size) (TSDF.generate_voxel_coords, :155-166), or
+ * at caller-supplied fp16 coordinates (3, X, Y, Z) (TSDF.from_file).  All arithmetic reproduces the reference's fp16
+ * torch ops: fp32 evaluation, one fp16 rounding per op.
+ *
+ * One call integrates up to DTB200_TSDF_MAX_FRAMES depth maps IN ORDER in a single pass over the volume (a voxel's
+ * update depends only on its own previous state), so the volume crosses HBM once per batch instead of once per frame.
+ * Per frame the caller supplies, as fp32 numbers that hold fp16 values exactly (computed with the reference's own
+ * small host-side ops): P = (K @ cam_T_world)[:3] and the frustum bounding box of get_frustum_bounds (:15-50).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define DTB200_TSDF_MAX_FRAMES 8
+#define DTB200_TSDF_SEMANTICS_ATEN_CPU 0  /* fp16 grid_sample as ATen's CPU build evaluates it (pinned by the fixtures) */
+#define DTB200_TSDF_SEMANTICS_ATEN_CUDA 1 /* ... as ATen's CUDA build does (fp32 un-normalise, saturating index cast) */
+
+typedef struct dtb200_tsdf_frame {
+  const void* depth;       /* fp16 (img_h, img_w) depth map; <= 0 = no measurement */
+  const uint8_t* mask;     /* optional (img_h, img_w) bytes: 0 = pixel invalid (reads as depth -1), or NULL */
+  float P[12];             /* rows 0..2 of fp16(K @ cam_T_world) */
+  float box_min[3], box_max[3]; /* fp16 frustum bounds in world space; only voxels strictly inside are touched */
+} dtb200_tsdf_frame;
+
+typedef struct dtb200_tsdf_integrate_params {
+  void* values;            /* fp16 (X, Y, Z), updated in place */
+  void* weights;           /* fp16 (X, Y, Z), updated in place */
+  const void* voxel_coords; /* fp16 (3, X, Y, Z) or NULL = generated from origin / voxel_size */
+  float origin[3];         /* fp32 origin (TSDF.from_bounds keeps it in fp32 until the coordinates are rounded) */
+  float voxel_size;
+  int32_t dims[3];
+  int32_t img_h, img_w;
+  int32_t num_frames;
+  int32_t semantics;       /* DTB200_TSDF_SEMANTICS_* */
+  float min_depth;         /* TSDFFuser.min_depth (0.5) */
+  float depth_range;       /* max_depth - min_depth, evaluated in double by the caller */
+  float max_depth_h;       /* fp16(max_depth) */
+  float truncation;        /* fp32(truncation_size * voxel_size) */
+  float trunc_check_h;     /* fp16(-truncation) or fp16(-1.5 * truncation) (extended_neg_truncation) */
+  dtb200_tsdf_frame frames[DTB200_TSDF_MAX_FRAMES];
+} dtb200_tsdf_integrate_params;
+
+int dtb200_tsdf_integrate(const dtb200_tsdf_integrate_params* p, dtb200_stream_t stream);
+
+/* out[n] = volume sampled at world point n (fp32 (N,3)); volume = fp16 (X, Y, Z); dims and origin_h are HOST arrays of 3
+ * (origin_h = fp16(origin) widened to fp32, as TSDF.origin is stored);
+ * mode 0 = trilinear ("bilinear" on a 5-D input), 1 = nearest; align_corners=True, zeros padding, fp32 coordinates
+ * (the reference's CPU branch, tools/tsdf.py:323-334). */
+int dtb200_tsdf_sample(const void* volume, const int32_t* dims, const float* origin_h, float voxel_size,
+                       const float* world_points, float* out, int64_t num_points, int32_t mode, dtb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,142 @@
+"""GPU parity of the TSDF kernels (csrc/tsdf.cu, through the C ABI and the doubletake_b200.tsdf mirror) against fixtures
+produced by executing the reference's tools/tsdf.py and against the numpy oracle.  fp16 volumes: BIT-EXACT."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as hp
+from doubletake_b200 import _lib as L
+from doubletake_b200 import tsdf as bt
+from oracle import oracle_tsdf as ot
+
+pytestmark = pytest.mark.gpu
+CASES = ["tsdf_room", "tsdf_room_mask_ext", "tsdf_near"]
+
+
+def bits(a):
+    if torch.is_tensor(a):
+        a = a.cpu().numpy()
+    return np.ascontiguousarray(a).view(np.uint16)
+
+
+def case_bounds(fx):
+    b = fx["bounds"]
+    return dict(xmin=b[0], xmax=b[1], ymin=b[2], ymax=b[3], zmin=b[4], zmax=b[5])
+
+
+def run_case(fx, explicit_grid=False, batch=None, semantics="aten_cpu"):
+    seed, nf, ih, iw, fb, with_mask, ext = [int(v) for v in fx["meta"]]
+    vol = bt.TSDF.from_bounds(case_bounds(fx), float(fx["voxel_size"]))
+    if explicit_grid:
+        vol._origin_f32 = None  # as after TSDF.from_file: the kernel reads the stored fp16 grid
+    fuser = bt.TSDFFuser(vol, max_depth=float(fx["max_depth"]), semantics=semantics)
+    batch = batch or fb
+    depth, T, K = (torch.from_numpy(fx[k]) for k in ("depth", "cam_T_world", "K"))
+    mask = torch.from_numpy(fx["mask"]) if with_mask else None
+    first = None
+    for s in range(0, nf, batch):
+        fuser.integrate_depth(depth[s:s + batch].cuda(), T[s:s + batch], K[s:s + batch],
+                              depth_mask_b1hw=None if mask is None else mask[s:s + batch].cuda(),
+                              extended_neg_truncation=bool(ext))
+        if s == 0 and batch == fb:
+            first = (vol.tsdf_values.clone(), vol.tsdf_weights.clone())
+    torch.cuda.synchronize()
+    return vol, first
+
+
+@pytest.mark.parametrize("explicit_grid", [False, True])
+@pytest.mark.parametrize("name", CASES)
+def test_integrate_matches_reference_fixture_bit_exact(name, explicit_grid):
+    fx = hp.load(name)
+    before = L.launch_count()
+    vol, first = run_case(fx, explicit_grid)
+    assert L.launch_count() > before
+    assert np.array_equal(bits(first[0]), bits(fx["values_first"])) and np.array_equal(bits(first[1]), bits(fx["weights_first"]))
+    dv = int((bits(vol.tsdf_values) != bits(fx["values"])).sum())
+    dw = int((bits(vol.tsdf_weights) != bits(fx["weights"])).sum())
+    assert dv == 0 and dw == 0, (dv, dw)
+
+
+@pytest.mark.parametrize("name", ["tsdf_room", "tsdf_near"])
+def test_frame_batching_does_not_change_a_bit(name):
+    """One pass over the volume for the whole batch == one pass per frame (a voxel depends only on its own history)."""
+    fx = hp.load(name)
+    nf = int(fx["meta"][1])
+    a, _ = run_case(fx, batch=nf)
+    b, _ = run_case(fx, batch=1)
+    assert torch.equal(a.tsdf_values, b.tsdf_values) and torch.equal(a.tsdf_weights, b.tsdf_weights)
+    assert np.array_equal(bits(a.tsdf_values), bits(fx["values"]))
+
+
+def test_more_frames_than_one_launch_holds():
+    """12 frames (> DTB200_TSDF_MAX_FRAMES) in one call, against the oracle."""
+    fx = hp.load("tsdf_room")
+    depth = np.concatenate([fx["depth"], fx["depth"][::-1]], 0)
+    T = np.concatenate([fx["cam_T_world"], fx["cam_T_world"][::-1]], 0)
+    K = np.concatenate([fx["K"], fx["K"]], 0)
+    assert depth.shape[0] > L.TSDF_MAX_FRAMES
+    vol = bt.TSDF.from_bounds(case_bounds(fx), float(fx["voxel_size"]))
+    bt.TSDFFuser(vol, max_depth=float(fx["max_depth"])).integrate_depth(
+        torch.from_numpy(depth.copy()).cuda(), torch.from_numpy(T.copy()), torch.from_numpy(K.copy()))
+    ref = ot.volume_from_bounds(case_bounds(fx), float(fx["voxel_size"]))
+    ot.integrate_depth(ref, depth, T, K, min_depth=0.5, max_depth=float(fx["max_depth"]))
+    assert np.array_equal(bits(vol.tsdf_values), bits(ref["tsdf_values"]))
+    assert np.array_equal(bits(vol.tsdf_weights), bits(ref["tsdf_weights"]))
+
+
+def test_aten_cuda_semantics_match_their_restatement():
+    fx = hp.load("tsdf_near")
+    vol, _ = run_case(fx, semantics="aten_cuda")
+    ref = ot.volume_from_bounds(case_bounds(fx), float(fx["voxel_size"]))
+    ot.integrate_depth(ref, fx["depth"], fx["cam_T_world"], fx["K"], min_depth=0.5, max_depth=float(fx["max_depth"]),
+                       semantics="cuda")
+    assert np.array_equal(bits(vol.tsdf_values), bits(ref["tsdf_values"]))
+    assert np.array_equal(bits(vol.tsdf_weights), bits(ref["tsdf_weights"]))
+    assert not np.array_equal(bits(vol.tsdf_weights), bits(fx["weights"]))  # the pinned build differs on overflowed pixels
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_sampling_matches_reference_fixture(name):
+    fx = hp.load(name)
+    vol = bt.TSDF.from_bounds(case_bounds(fx), float(fx["voxel_size"]))
+    vol.tsdf_values = torch.from_numpy(fx["values"]).cuda()
+    vol.tsdf_weights = torch.from_numpy(fx["weights"]).cuda()
+    pts = torch.from_numpy(fx["points"]).cuda()
+    for what in ("weights", "tsdf"):
+        for mode in ("bilinear", "nearest"):
+            got = vol.sample_tsdf(pts, what_to_sample=what, sampling_method=mode).cpu().numpy()
+            ref = fx[f"sample_{what}_{mode}"]
+            assert got.shape == ref.shape
+            assert np.array_equal(got, ref), (what, mode, float(np.abs(got - ref).max()))
+
+
+def test_reference_default_volume_lazy_grid():
+    """The reference's default fusion volume (20 m cube at 4 cm, fusers_helper.py:50-61: 504^3 = 128 M voxels) with the
+    grid regenerated in registers: voxels outside the frustum box stay untouched, a second identical frame moves every
+    touched voxel's weight, and a cropped region equals the oracle run on the crop's own volume."""
+    fx = hp.load("tsdf_room")
+    big = bt.TSDF.from_bounds(dict(xmin=-10.0, xmax=10.0, ymin=-10.0, ymax=10.0, zmin=-10.0, zmax=10.0), 0.04, lazy_grid=True)
+    assert tuple(big.tsdf_values.shape) == (504, 504, 504)
+    fuser = bt.TSDFFuser(big, max_depth=float(fx["max_depth"]))
+    depth, T, K = (torch.from_numpy(fx[k]) for k in ("depth", "cam_T_world", "K"))
+    fuser.integrate_depth(depth[:2].cuda(), T[:2], K[:2])
+    torch.cuda.synchronize()
+    touched = big.tsdf_weights > 0
+    n = int(touched.sum())
+    assert 10000 < n < 5_000_000
+    assert bool((big.tsdf_values[~touched] == -1).all())
+    # oracle on a crop: same grid formula, so voxel (i,j,k) of the crop is voxel (i0+i, j0+j, k0+k) of the big volume
+    idx = touched.nonzero()
+    lo = [int(v) // 8 * 8 for v in idx.min(0).values.tolist()]
+    hi = [min(504, (int(v) // 8 + 1) * 8) for v in idx.max(0).values.tolist()]
+    dims = [h - l for l, h in zip(lo, hi)]
+    origin = np.array([-10.0, -10.0, -10.0], np.float32)
+    gx, gy, gz = np.meshgrid(*[np.arange(l, h) for l, h in zip(lo, hi)], indexing="ij")
+    grid = np.stack([gx, gy, gz], 0).astype(np.float32)
+    coords = (origin.reshape(3, 1, 1, 1) + (grid * np.float32(0.04)).astype(np.float32)).astype(np.float32).astype(np.float16)
+    ref = dict(voxel_coords_3hwd=coords, tsdf_values=-np.ones(dims, np.float16), tsdf_weights=np.zeros(dims, np.float16),
+               origin=origin.astype(np.float16), voxel_size=0.04)
+    ot.integrate_depth(ref, fx["depth"][:2], fx["cam_T_world"][:2], fx["K"][:2], min_depth=0.5, max_depth=float(fx["max_depth"]))
+    crop = (slice(lo[0], hi[0]), slice(lo[1], hi[1]), slice(lo[2], hi[2]))
+    assert np.array_equal(bits(big.tsdf_values[crop]), bits(ref["tsdf_values"]))
+    assert np.array_equal(bits(big.tsdf_weights[crop]), bits(ref["tsdf_weights"]))

@@ -1,0 +1,104 @@
+"""Pin the TSDF oracle (oracle/oracle_tsdf.py) and the host side of doubletake_b200.tsdf against fixtures produced by
+executing the real reference tools/tsdf.py (oracle/make_golden_tsdf.py).  CPU only.  fp16 volumes: BIT-EXACT."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as hp
+from doubletake_b200 import tsdf as bt
+from oracle import oracle_tsdf as ot
+
+CASES = ["tsdf_room", "tsdf_room_mask_ext", "tsdf_near"]
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint16)
+
+
+def case_bounds(fx):
+    b = fx["bounds"]
+    return dict(xmin=b[0], xmax=b[1], ymin=b[2], ymax=b[3], zmin=b[4], zmax=b[5])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_integrate_is_bit_exact(name):
+    fx = hp.load(name)
+    seed, nf, ih, iw, batch, with_mask, ext = [int(v) for v in fx["meta"]]
+    vol = ot.volume_from_bounds(case_bounds(fx), float(fx["voxel_size"]))
+    assert np.array_equal(bits(vol["voxel_coords_3hwd"]), bits(fx["voxel_coords"]))
+    assert np.array_equal(bits(vol["origin"]), bits(fx["origin"]))
+    for s in range(0, nf, batch):
+        ot.integrate_depth(vol, fx["depth"][s:s + batch], fx["cam_T_world"][s:s + batch], fx["K"][s:s + batch],
+                           min_depth=float(fx["min_depth"]), max_depth=float(fx["max_depth"]),
+                           depth_mask_b1hw=fx["mask"][s:s + batch] if with_mask else None, extended_neg_truncation=bool(ext))
+        if s == 0:
+            assert np.array_equal(bits(vol["tsdf_values"]), bits(fx["values_first"]))
+            assert np.array_equal(bits(vol["tsdf_weights"]), bits(fx["weights_first"]))
+    assert np.array_equal(bits(vol["tsdf_values"]), bits(fx["values"]))
+    assert np.array_equal(bits(vol["tsdf_weights"]), bits(fx["weights"]))
+    assert int((fx["weights"] > 0).sum()) > 10000  # the case really fuses something
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_sampling_is_bit_exact(name):
+    fx = hp.load(name)
+    vol = dict(tsdf_values=fx["values"], tsdf_weights=fx["weights"], origin=fx["origin"], voxel_size=float(fx["voxel_size"]))
+    for what in ("weights", "tsdf"):
+        for mode in ("bilinear", "nearest"):
+            got = ot.sample_volume(vol, fx["points"], what, mode)
+            assert np.array_equal(got, fx[f"sample_{what}_{mode}"]), (what, mode)
+
+
+def test_nonfinite_pixel_coordinates_follow_the_pinned_build():
+    """tsdf_near holds voxels whose projected pixel overflows fp16: ATen's CPU build reads row / column 0 there (pinned),
+    its CUDA build reads the zero padding -- the two semantics must differ on exactly such voxels and nowhere else."""
+    fx = hp.load("tsdf_near")
+    res = {}
+    for sem in ("cpu", "cuda"):
+        vol = ot.volume_from_bounds(case_bounds(fx), float(fx["voxel_size"]))
+        ot.integrate_depth(vol, fx["depth"], fx["cam_T_world"], fx["K"], min_depth=float(fx["min_depth"]),
+                           max_depth=float(fx["max_depth"]), semantics=sem)
+        res[sem] = vol["tsdf_weights"].copy()
+    assert np.array_equal(bits(res["cpu"]), bits(fx["weights"]))
+    diff = int((bits(res["cpu"]) != bits(res["cuda"])).sum())
+    assert 0 < diff < 100
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_mirror_grid_and_frame_constants(name):
+    """doubletake_b200.tsdf on the host: same grid as the reference's from_bounds; the per-frame constants handed to the
+    kernel (P, frustum box) equal the oracle's bit for bit."""
+    fx = hp.load(name)
+    vol = bt.TSDF.from_bounds(case_bounds(fx), float(fx["voxel_size"]))
+    assert np.array_equal(bits(vol.voxel_coords_3hwd.numpy()), bits(fx["voxel_coords"]))
+    assert np.array_equal(bits(vol.origin.numpy()), bits(fx["origin"]))
+    assert tuple(vol.tsdf_values.shape) == fx["values"].shape and float(vol.tsdf_values.float().max()) == -1.0
+    fuser = bt.TSDFFuser(vol, max_depth=float(fx["max_depth"]))
+    ih, iw = fx["depth"].shape[2:]
+    for b in range(fx["depth"].shape[0]):
+        K, T = torch.from_numpy(fx["K"][b]), torch.from_numpy(fx["cam_T_world"][b])
+        P, lo, hi = fuser._frame_constants(T, K, ih, iw)
+        trunc = 3.0 * float(fx["voxel_size"])
+        invK = np.linalg.inv(fx["K"][b].astype(np.float32)).astype(np.float16)
+        wTc = np.linalg.inv(fx["cam_T_world"][b].astype(np.float32)).astype(np.float16)
+        olo, ohi = ot.frustum_bounds(invK, wTc, 0.01, float(fx["max_depth"]) + trunc + 0.1, ih, iw)
+        oP = ot.matmul_h(fx["K"][b], fx["cam_T_world"][b])[:3]
+        assert np.array_equal(np.float32(P), oP.astype(np.float32).ravel())
+        assert np.array_equal(np.float32(lo), olo.astype(np.float32)) and np.array_equal(np.float32(hi), ohi.astype(np.float32))
+
+
+def test_mirror_rejects_cpu_and_bad_arguments(tmp_path):
+    vol = bt.TSDF.from_bounds(dict(xmin=0, xmax=0.5, ymin=0, ymax=0.5, zmin=0, zmax=0.5), 0.05)
+    with pytest.raises(RuntimeError):
+        bt.TSDFFuser(vol, use_gpu=False)
+    with pytest.raises(KeyError):
+        bt.TSDF.from_bounds(dict(xmin=0), 0.05)
+    with pytest.raises(ValueError):
+        vol.sample_tsdf(torch.zeros(4, 2))
+    with pytest.raises(NotImplementedError):
+        vol.to_mesh()
+    path = str(tmp_path / "v.npz")
+    vol.save_tsdf(path)
+    back = bt.TSDF.from_file(path)
+    assert torch.equal(back.voxel_coords_3hwd, vol.voxel_coords_3hwd) and back.voxel_size == vol.voxel_size
+    assert back._origin_f32 is None  # a loaded grid is read from memory, not regenerated

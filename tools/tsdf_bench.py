@@ -1,0 +1,72 @@
+"""Timing of the TSDF kernels on the reference's default fusion volume (20 m cube at 4 cm = 504^3 voxels), GPU only.
+
+    python tools/tsdf_bench.py [--reps 10]
+Prints, per batch size, the kernel time, the voxels touched and the achieved HBM bandwidth over the ALGORITHMIC bytes
+(8 bytes per touched voxel: fp16 value + weight read and written; the coordinate grid is regenerated in registers)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from doubletake_b200 import tsdf as bt  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=10)
+    args = ap.parse_args()
+    peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+    fx = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "tsdf_room.npz"))
+    depth, T, K = (torch.from_numpy(fx[k]) for k in ("depth", "cam_T_world", "K"))
+    # a 480x640 depth map of the same scene (nearest up-sampling x5) and intrinsics scaled to it
+    depth = torch.nn.functional.interpolate(depth.float(), scale_factor=5, mode="nearest").half().cuda()
+    K = K.float().clone()
+    K[:, :2] *= 5
+    K = K.half()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for nb in (1, 6):
+        vol = bt.TSDF.from_bounds(dict(xmin=-10.0, xmax=10.0, ymin=-10.0, ymax=10.0, zmin=-10.0, zmax=10.0), 0.04, lazy_grid=True)
+        fuser = bt.TSDFFuser(vol, max_depth=3.0)
+        fuser.integrate_depth(depth[:nb], T[:nb], K[:nb])
+        torch.cuda.synchronize()
+        touched = int((vol.tsdf_weights > 0).sum())
+        ts = []
+        for _ in range(args.reps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fuser.integrate_depth(depth[:nb], T[:nb], K[:nb])
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        ms = sorted(ts)[len(ts) // 2]
+        gbs = 8.0 * touched / (ms * 1e-3) / 1e9
+        print(f"integrate {nb} frame(s) 480x640 into 504^3: {ms * 1e3:8.1f} us (host constants + 1 launch), {touched} voxels touched, "
+              f"{gbs:7.1f} GB/s of algorithmic bytes = {gbs / peaks['hbm_gbs'] * 100:.1f} % of the measured HBM peak; "
+              f"{vol.tsdf_values.numel() / (ms * 1e-3) / 1e9:.1f} G voxels/s scanned")
+        del vol, fuser
+    vol = bt.TSDF.from_bounds(dict(xmin=-10.0, xmax=10.0, ymin=-10.0, ymax=10.0, zmin=-10.0, zmax=10.0), 0.04, lazy_grid=True)
+    pts = (torch.rand(480 * 640, 3, device="cuda") - 0.5) * 6.0
+    vol.sample_tsdf(pts, "weights")
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(args.reps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        vol.sample_tsdf(pts, "weights")
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ms = sorted(ts)[len(ts) // 2]
+    print(f"sample 480x640 points (trilinear, weights): {ms * 1e3:8.1f} us, {pts.shape[0] * (12 + 4 + 16) / (ms * 1e-3) / 1e9:.1f} GB/s "
+          f"of algorithmic bytes (12 B point + 8 x 2 B taps + 4 B out)")
+
+
+if __name__ == "__main__":
+    main()
