@@ -64,6 +64,7 @@ class TsdfIntegrateParams(C.Structure):
     _fields_ = [
         ("values", fp), ("weights", fp), ("voxel_coords", fp),
         ("origin", C.c_float * 3), ("voxel_size", C.c_float), ("dims", C.c_int32 * 3),
+        ("vox_begin", C.c_int32 * 3), ("vox_end", C.c_int32 * 3),
         ("img_h", C.c_int32), ("img_w", C.c_int32), ("num_frames", C.c_int32), ("semantics", C.c_int32),
         ("min_depth", C.c_float), ("depth_range", C.c_float), ("max_depth_h", C.c_float), ("truncation", C.c_float),
         ("trunc_check_h", C.c_float),

@@ -177,6 +177,24 @@ class TSDFFuser:
         P = _matmul_h(K_44, cam_T_world_44)[:3]
         return P.float().flatten().tolist(), lo.float().tolist(), hi.float().tolist()
 
+    def _index_box(self, lo, hi, dims, margin=2):
+        """Conservative index cover [begin, end) of the voxels whose fp16 coordinate can lie strictly inside (lo, hi):
+        coordinates grow monotonically with the index and fp16 rounding moves them by far less than ``margin`` voxels.
+        Caller-supplied grids (TSDF.from_file) and non-finite boxes scan the whole volume; z bounds are multiples of 8."""
+        full = [0, 0, 0], list(dims)
+        if self.tsdf._origin_f32 is None or not all(np.isfinite(lo + hi)):
+            return full
+        begin, end = [], []
+        for a in range(3):
+            o, vs = float(self.tsdf._origin_f32[a]), float(self.voxel_size)
+            b = int(np.floor((lo[a] - o) / vs)) - margin
+            e = int(np.ceil((hi[a] - o) / vs)) + margin + 1
+            begin.append(min(max(b, 0), dims[a]))
+            end.append(min(max(e, 0), dims[a]))
+        begin[2] = begin[2] // 8 * 8
+        end[2] = min((end[2] + 7) // 8 * 8, dims[2])
+        return begin, end
+
     def integrate_depth(self, depth_b1hw, cam_T_world_T_b44, K_b44, depth_mask_b1hw=None, extended_neg_truncation=False):
         """Integrates a batch of depth maps into the volume, in order (tools/tsdf.py:414-558)."""
         self.tsdf.cuda()
@@ -204,16 +222,23 @@ class TSDFFuser:
         p.max_depth_h = float(torch.tensor(self.max_depth).half())
         p.truncation = float(self.truncation)
         p.trunc_check_h = float(torch.tensor(-self.truncation * (1.5 if extended_neg_truncation else 1.0)).half())
+        dims = tuple(values.shape)
         for s in range(0, B, L.TSDF_MAX_FRAMES):
             n = min(L.TSDF_MAX_FRAMES, B - s)
             p.num_frames = n
+            begin, end = list(dims), [0, 0, 0]
             for i in range(n):
                 P, lo, hi = self._frame_constants(T_cpu[s + i], K_cpu[s + i], img_h, img_w)
+                b_i, e_i = self._index_box(lo, hi, dims)
+                begin = [min(a, b) for a, b in zip(begin, b_i)]
+                end = [max(a, b) for a, b in zip(end, e_i)]
                 fr = p.frames[i]
                 fr.depth = depth[s + i].data_ptr()
                 fr.mask = None if mask is None else mask[s + i].data_ptr()
                 fr.P = (C.c_float * 12)(*P)
                 fr.box_min = (C.c_float * 3)(*lo)
                 fr.box_max = (C.c_float * 3)(*hi)
+            end = [max(b, e) for b, e in zip(begin, end)]  # empty cover -> empty box
+            p.vox_begin, p.vox_end = (C.c_int32 * 3)(*begin), (C.c_int32 * 3)(*end)
             L.check(L.lib().dtb200_tsdf_integrate(C.byref(p), L.stream()))
         # `depth` / `mask` stay referenced until the launches are enqueued; the caching allocator keeps them valid on this stream

@@ -236,6 +236,8 @@ typedef struct dtb200_tsdf_integrate_params {
   float origin[3];         /* fp32 origin (TSDF.from_bounds keeps it in fp32 until the coordinates are rounded) */
   float voxel_size;
   int32_t dims[3];
+  int32_t vox_begin[3], vox_end[3]; /* index box [begin, end) the launch scans (z bounds multiples of 8): any conservative
+                                       cover of the frames' frustum boxes; {0,0,0} / dims scans the whole volume */
   int32_t img_h, img_w;
   int32_t num_frames;
   int32_t semantics;       /* DTB200_TSDF_SEMANTICS_* */

@@ -102,3 +102,31 @@ def test_mirror_rejects_cpu_and_bad_arguments(tmp_path):
     back = bt.TSDF.from_file(path)
     assert torch.equal(back.voxel_coords_3hwd, vol.voxel_coords_3hwd) and back.voxel_size == vol.voxel_size
     assert back._origin_f32 is None  # a loaded grid is read from memory, not regenerated
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_index_box_covers_every_voxel_of_the_frustum_box(name):
+    """The launch scans only TSDFFuser._index_box: it must contain every voxel whose fp16 coordinate passes the reference's
+    strict box test (and stay well below the whole volume for a camera inside a large one)."""
+    fx = hp.load(name)
+    vol = bt.TSDF.from_bounds(case_bounds(fx), float(fx["voxel_size"]))
+    fuser = bt.TSDFFuser(vol, max_depth=float(fx["max_depth"]))
+    ih, iw = fx["depth"].shape[2:]
+    c = fx["voxel_coords"].astype(np.float32)
+    dims = c.shape[1:]
+    for b in range(fx["depth"].shape[0]):
+        _, lo, hi = fuser._frame_constants(torch.from_numpy(fx["cam_T_world"][b]), torch.from_numpy(fx["K"][b]), ih, iw)
+        begin, end = fuser._index_box(lo, hi, dims)
+        assert begin[2] % 8 == 0 and end[2] % 8 == 0 and all(0 <= bb <= ee <= d for bb, ee, d in zip(begin, end, dims))
+        inside = np.ones(dims, bool)
+        for a in range(3):
+            inside &= (c[a] > np.float32(lo[a])) & (c[a] < np.float32(hi[a]))
+        idx = np.argwhere(inside)
+        assert len(idx) > 0
+        assert all(idx[:, a].min() >= begin[a] and idx[:, a].max() < end[a] for a in range(3))
+    big = bt.TSDF(None, torch.zeros(8, 8, 8), torch.zeros(8, 8, 8), 0.04, torch.tensor([-10.0, -10.0, -10.0]),
+                  _origin_f32=torch.tensor([-10.0, -10.0, -10.0]))
+    bf = bt.TSDFFuser(big, max_depth=3.0)
+    begin, end = bf._index_box(lo, hi, (504, 504, 504))
+    assert np.prod([e - b for b, e in zip(begin, end)]) < 0.05 * 504 ** 3
+    assert bf._index_box([float("nan")] * 3, hi, (504, 504, 504)) == ([0, 0, 0], [504, 504, 504])
