@@ -45,6 +45,26 @@ def get_frustum_bounds(invK_44, world_T_cam_44, min_depth=0.1, max_depth=10.0, i
     return world.amin(dim=1)[:3], world.amax(dim=1)[:3]
 
 
+def _matmul_h_np(a, b):
+    """numpy twin of ``_matmul_h`` for the per-frame constants."""
+    a32, b32 = a.astype(np.float32), b.astype(np.float32)
+    acc = np.zeros(a32.shape[:-1] + b32.shape[-1:], dtype=np.float32)
+    for k in range(a32.shape[-1]):
+        acc = (acc + a32[..., :, k:k + 1] * b32[..., k:k + 1, :]).astype(np.float32)
+    return acc.astype(np.float16)
+
+
+def _frustum_bounds_np(invK, world_T_cam, min_depth, max_depth, img_h, img_w):
+    """numpy twin of ``get_frustum_bounds`` (fp16 in, fp16 out)."""
+    corners = np.array([[0, 0, 1, 1], [img_w, 0, 1, 1], [0, img_h, 1, 1], [img_w, img_h, 1, 1]], dtype=np.float16).T
+    pts = _matmul_h_np(invK, corners)
+    near, far = pts.copy(), pts.copy()
+    near[:3] = (near[:3].astype(np.float32) * np.float32(min_depth)).astype(np.float16)
+    far[:3] = (far[:3].astype(np.float32) * np.float32(max_depth)).astype(np.float16)
+    world = _matmul_h_np(world_T_cam, np.concatenate([near, far], 1))
+    return world.min(1)[:3], world.max(1)[:3]
+
+
 class TSDF:
     """reference ``TSDF`` (tools/tsdf.py:53-337): fp16 voxel grid, values, weights."""
 
@@ -169,13 +189,16 @@ class TSDFFuser:
     truncation = property(lambda self: self.truncation_size * self.tsdf.voxel_size)
 
     def _frame_constants(self, cam_T_world_44, K_44, img_h, img_w):
-        """Per-frame host constants with the reference's own small fp16 ops (tools/tsdf.py:444-450,398-407)."""
+        """Per-frame host constants with the reference's own small fp16 ops (tools/tsdf.py:444-450,398-407): fp32 inverses
+        rounded to fp16, the frustum box, P = (K @ cam_T_world)[:3].  numpy on 4x4 arrays (a few tens of microseconds)."""
+        K = np.asarray(K_44, dtype=np.float16)
+        T = np.asarray(cam_T_world_44, dtype=np.float16)
         depth_max = self.max_depth + self.truncation + 0.1
-        invK = torch.inverse(K_44.float()).half()
-        world_T_cam = torch.inverse(cam_T_world_44.float()).half()
-        lo, hi = get_frustum_bounds(invK, world_T_cam, 0.01, depth_max, img_h, img_w)
-        P = _matmul_h(K_44, cam_T_world_44)[:3]
-        return P.float().flatten().tolist(), lo.float().tolist(), hi.float().tolist()
+        invK = np.linalg.inv(K.astype(np.float32)).astype(np.float32).astype(np.float16)
+        world_T_cam = np.linalg.inv(T.astype(np.float32)).astype(np.float32).astype(np.float16)
+        lo, hi = _frustum_bounds_np(invK, world_T_cam, 0.01, depth_max, img_h, img_w)
+        P = _matmul_h_np(K, T)[:3]
+        return P.astype(np.float32).ravel().tolist(), lo.astype(np.float32).tolist(), hi.astype(np.float32).tolist()
 
     def _index_box(self, lo, hi, dims, margin=2):
         """Conservative index cover [begin, end) of the voxels whose fp16 coordinate can lie strictly inside (lo, hi):
@@ -205,7 +228,7 @@ class TSDFFuser:
         depth = depth_b1hw.to(dev).half().contiguous()
         mask = None if depth_mask_b1hw is None else depth_mask_b1hw.to(dev).to(torch.uint8).contiguous()
         B, _, img_h, img_w = depth.shape
-        T_cpu, K_cpu = cam_T_world_T_b44.detach().cpu().half(), K_b44.detach().cpu().half()
+        T_cpu, K_cpu = cam_T_world_T_b44.detach().cpu().half().numpy(), K_b44.detach().cpu().half().numpy()
         p = L.TsdfIntegrateParams()
         p.values, p.weights = L.ptr(values), L.ptr(weights)
         if self.tsdf._origin_f32 is not None:
