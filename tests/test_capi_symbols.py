@@ -33,13 +33,13 @@ def test_every_declared_symbol_is_exported_and_bound():
 def _struct_fields(name):
     text = open(os.path.join(ROOT, "include", "doubletake_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    structs = dict((n, b) for b, n in re.findall(r"typedef struct \{((?:(?!typedef).)*?)\} (\w+);", text, flags=re.S))
+    structs = dict((n, b) for b, n in re.findall(r"typedef struct(?: \w+)? \{((?:(?!typedef).)*?)\} (\w+);", text, flags=re.S))
     names = []
     for decl in structs[name].split(";"):
         decl = decl.strip()
         if not decl:
             continue
-        decl = re.sub(r"^(const\s+)?(float|int32_t|uint8_t|uint64_t|void)\s*\*?", "", decl).strip()
+        decl = re.sub(r"^(const\s+)?(float|int32_t|uint8_t|uint64_t|void|dtb200_tsdf_frame)\s*\*?", "", decl).strip()
         for part in decl.split(","):
             names.append(re.sub(r"\[.*\]", "", part.replace("*", "")).strip())
     return names
@@ -48,6 +48,33 @@ def _struct_fields(name):
 def test_struct_layout_matches_header_field_order():
     assert _struct_fields("dtb200_conv_params") == [f[0] for f in _lib.ConvParams._fields_]
     assert _struct_fields("dtb200_cost_volume_params") == [f[0] for f in _lib.CostVolumeParams._fields_]
+    assert _struct_fields("dtb200_tsdf_frame") == [f[0] for f in _lib.TsdfFrame._fields_]
+    assert _struct_fields("dtb200_tsdf_integrate_params") == [f[0] for f in _lib.TsdfIntegrateParams._fields_]
+
+
+def test_struct_sizes_and_offsets_match_the_c_compiler(tmp_path):
+    """sizeof / offsetof of every ABI struct as gcc lays them out == the ctypes mirrors (catches a wrong field TYPE, which
+    the name comparison above cannot)."""
+    import subprocess
+
+    pairs = [("dtb200_conv_params", _lib.ConvParams), ("dtb200_cost_volume_params", _lib.CostVolumeParams),
+             ("dtb200_tsdf_frame", _lib.TsdfFrame), ("dtb200_tsdf_integrate_params", _lib.TsdfIntegrateParams)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "doubletake_b200.h")}"',
+             "int main(void) {"]
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
 
 
 def test_errors_are_reported_without_a_gpu():
@@ -56,3 +83,30 @@ def test_errors_are_reported_without_a_gpu():
     assert rc == -1 and b"null params" in lib.dtb200_last_error()
     rc = lib.dtb200_cost_volume(None, None)
     assert rc == -1
+
+
+def test_tsdf_argument_validation_without_a_gpu():
+    """Every rejection happens before the first CUDA call, so it is testable here."""
+    lib = _lib.lib()
+    assert lib.dtb200_tsdf_integrate(None, None) == -1
+    p = _lib.TsdfIntegrateParams()
+    p.values, p.weights = 16, 32  # never dereferenced: validation fails first
+    p.num_frames = 9
+    assert lib.dtb200_tsdf_integrate(ctypes.byref(p), None) == -1 and b"num_frames" in lib.dtb200_last_error()
+    p.num_frames = 1
+    p.dims = (ctypes.c_int32 * 3)(16, 16, 12)
+    assert lib.dtb200_tsdf_integrate(ctypes.byref(p), None) == -1 and b"multiples of 8" in lib.dtb200_last_error()
+    p.dims = (ctypes.c_int32 * 3)(16, 16, 16)
+    p.img_h, p.img_w = 4, 4
+    p.semantics = 7
+    assert lib.dtb200_tsdf_integrate(ctypes.byref(p), None) == -1 and b"semantics" in lib.dtb200_last_error()
+    p.semantics = 0
+    assert lib.dtb200_tsdf_integrate(ctypes.byref(p), None) == -1 and b"no depth map" in lib.dtb200_last_error()
+    p.frames[0].depth = 64
+    p.vox_begin, p.vox_end = (ctypes.c_int32 * 3)(0, 0, 4), (ctypes.c_int32 * 3)(16, 16, 16)
+    assert lib.dtb200_tsdf_integrate(ctypes.byref(p), None) == -1 and b"vox_begin" in lib.dtb200_last_error()
+    p.vox_begin, p.vox_end = (ctypes.c_int32 * 3)(8, 8, 8), (ctypes.c_int32 * 3)(8, 8, 8)
+    assert lib.dtb200_tsdf_integrate(ctypes.byref(p), None) == 0  # empty box: nothing to launch
+    dims, origin = (ctypes.c_int32 * 3)(16, 16, 16), (ctypes.c_float * 3)(0, 0, 0)
+    assert lib.dtb200_tsdf_sample(16, dims, origin, 0.04, 16, 16, 10, 5, None) == -1 and b"mode" in lib.dtb200_last_error()
+    assert lib.dtb200_tsdf_sample(None, dims, origin, 0.04, 16, 16, 10, 0, None) == -1
