@@ -53,15 +53,26 @@ struct TcCfg {
 //          weight-ring stage instead of 3
 //   bits 8..12: timing knock-outs of the tensor-core conv pipeline (results are WRONG; tools/conv_bench.py --debug)
 static int g_flags = -1;
+// the timing knock-outs (bits 8 and up) make the kernels skip work, i.e. produce WRONG results: they are honoured only
+// when DTB200_DEVELOPMENT=1 is set in the environment (tools/conv_bench.py sets it), never by a stray debug_set call
+static int sanitize_flags(int flags) {
+  static int dev = -1;
+  if (dev < 0) {
+    const char* e = getenv("DTB200_DEVELOPMENT");
+    dev = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  if (flags < 0) flags = 0;
+  return dev ? flags : (flags & 0xff);
+}
 static int conv_flags() {
   if (g_flags < 0) {
     const char* e = getenv("DTB200_CONV_FLAGS");
-    g_flags = e ? atoi(e) : 0;
+    g_flags = sanitize_flags(e ? atoi(e) : 0);
   }
   return g_flags;
 }
 int conv_tc_debug_set(int flags) {
-  g_flags = flags < 0 ? 0 : flags;
+  g_flags = sanitize_flags(flags);
   return DTB200_OK;
 }
 

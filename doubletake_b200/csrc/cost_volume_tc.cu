@@ -62,8 +62,6 @@ __global__ void __launch_bounds__(kTThreads, 1) cv_mlp_tc_kernel(const dtb200_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int K = p.views;
-  const int F = 26 * K + 20;
-  const int nvis = kC * (K + 1);
   const int nmeta = 10 * K + 4;
   const int nkb1 = cvtc_nkb1(K);
   const int nkb = nkb1 + 4;

@@ -33,7 +33,8 @@ typedef void* dtb200_stream_t; /* cudaStream_t */
 #define DTB200_MAX_VIEWS 16
 
 int dtb200_abi_version(void);
-/* development only: knock-out switches for the tensor-core conv pipeline (0 = normal operation) */
+/* development only: kernel-variant switches of the tensor-core conv pipeline (0 = normal operation); the timing
+ * knock-outs (bits 8 and up, wrong results by design) are ignored unless DTB200_DEVELOPMENT=1 is in the environment */
 int dtb200_debug_set(int flags);
 const char* dtb200_last_error(void);
 /* number of kernels this library has launched from the calling process (bench.py's gpu_launches claim) */
