@@ -31,6 +31,45 @@ def shard_scans(scan_lengths, rank: int, world_size: int):
     return sorted(mine)
 
 
+def read_frame_tuples(path, limit_to_scan_id=None, skip_to_frame=None, skip_frames=None):
+    """Keyframe tuples of a reference tuple file (``scan_id frame_id_0 frame_id_1 ... frame_id_N-1`` per line, frame 0 the
+    reference view; datasets/generic_mvs_dataset.py:29-37,149-180, incl. its scan filter / skip options).
+    Returns a list of (scan_id, [frame ids]) in file order."""
+    with open(path) as f:
+        lines = f.read().splitlines()
+    if limit_to_scan_id is not None:
+        lines = [ln for ln in lines if ln.split(" ")[0] == limit_to_scan_id]
+    if skip_to_frame is not None:
+        lines = lines[skip_to_frame:]
+    if skip_frames is not None:
+        lines = lines[::skip_frames]
+    out = []
+    for ln in lines:
+        scan_id, *frame_ids = ln.split(" ")
+        out.append((scan_id, frame_ids))
+    return out
+
+
+def shard_tuples(tuples, rank: int, world_size: int, by: str = "frame"):
+    """Indices (into ``tuples``) of the keyframes this rank processes, in processing order.
+
+    ``by="frame"``: round-robin over keyframes (independent frames: test_no_hint / offline passes; BASELINE cfg 4).
+    ``by="scan"``: whole scans, longest first (incremental mode: a frame's hint comes from the TSDF fused from the
+    earlier frames of ITS scan, test_incremental.py:186-269); frames keep their order inside a scan."""
+    if by == "frame":
+        return shard_frames(len(tuples), rank, world_size)
+    if by != "scan":
+        raise ValueError("by must be 'frame' or 'scan'")
+    scans, members = [], {}
+    for i, (scan_id, _) in enumerate(tuples):
+        if scan_id not in members:
+            members[scan_id] = []
+            scans.append(scan_id)
+        members[scan_id].append(i)
+    mine = shard_scans([len(members[s]) for s in scans], rank, world_size)
+    return [i for k in mine for i in members[scans[k]]]
+
+
 def gather_depth_maps(local_depth: torch.Tensor, num_frames: int, group=None):
     """Gather per-rank depth maps (n_local,1,H,W) into frame order (num_frames,1,H,W) on every rank.
 
