@@ -33,15 +33,16 @@ def _matmul_h(a, b):
     return acc.half()
 
 
-def get_frustum_bounds(invK_44, world_T_cam_44, min_depth=0.1, max_depth=10.0, img_h=480, img_w=640):
-    """reference tools/tsdf.py:15-50 on fp16 CPU matrices: world-space bounding box of the view frustum."""
+def get_frustum_bounds(invK_144, world_T_cam_144, min_depth=0.1, max_depth=10.0, img_h=480, img_w=640):
+    """reference tools/tsdf.py:15-50 on fp16 CPU matrices ((4,4), as the reference's caller passes them): world-space
+    bounding box of the view frustum."""
     corners = torch.tensor([[0, 0, 1, 1], [img_w, 0, 1, 1], [0, img_h, 1, 1], [img_w, img_h, 1, 1]],
-                           dtype=invK_44.dtype).T
-    pts = _matmul_h(invK_44, corners)
+                           dtype=invK_144.dtype).T
+    pts = _matmul_h(invK_144, corners)
     near, far = pts.clone(), pts.clone()
     near[:3] *= min_depth
     far[:3] *= max_depth
-    world = _matmul_h(world_T_cam_44, torch.cat((near, far), dim=1))
+    world = _matmul_h(world_T_cam_144, torch.cat((near, far), dim=1))
     return world.amin(dim=1)[:3], world.amax(dim=1)[:3]
 
 

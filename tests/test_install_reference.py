@@ -10,6 +10,7 @@ import pytest
 import torch
 
 REF = "/root/reference/src"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
 
 
@@ -50,3 +51,43 @@ def test_install_swaps_modules_and_keeps_weights(decoder):
         assert torch.equal(got[k], want[k]), k
     # strict loading of a reference checkpoint into the swapped model works too
     m.load_state_dict(want, strict=True)
+
+
+def test_tsdf_mirror_has_the_reference_signatures():
+    """doubletake_b200.tsdf against the REAL reference classes (tools/tsdf.py, imported with the stubs of oracle/ref_stubs):
+    every mirrored method takes the reference's parameters, in the reference's order, with the reference's defaults."""
+    import inspect
+    import types
+
+    if not os.path.exists("/root/reference/src/doubletake/tools/tsdf.py"):
+        pytest.skip("reference tree not present (GPU box)")
+    for pth in (os.path.join(ROOT, "oracle", "ref_stubs"), "/root/reference/src"):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    if "doubletake.utils.pytorch3d_extras" not in sys.modules:
+        m = types.ModuleType("doubletake.utils.pytorch3d_extras")
+        m.marching_cubes = None
+        sys.modules["doubletake.utils.pytorch3d_extras"] = m
+    from doubletake.tools import tsdf as ref
+    from doubletake_b200 import tsdf as ours
+
+    def params(fn):
+        return [(n, p.default) for n, p in inspect.signature(fn).parameters.items()]
+
+    for cls, names in (("TSDF", ["__init__", "from_file", "from_mesh", "generate_voxel_coords", "cuda", "cpu", "save_tsdf",
+                                 "sample_tsdf"]),
+                       ("TSDFFuser", ["integrate_depth"])):
+        for name in names:
+            want = params(getattr(getattr(ref, cls), name))
+            got = params(getattr(getattr(ours, cls), name))
+            assert got[: len(want)] == want, (cls, name, got, want)  # extensions may only be appended, with defaults
+            assert all(d is not inspect.Parameter.empty for _, d in got[len(want):]), (cls, name)
+    # from_bounds / TSDFFuser.__init__: same leading parameters, one appended keyword each (lazy_grid, semantics)
+    assert params(ours.TSDF.from_bounds)[:2] == params(ref.TSDF.from_bounds)
+    assert params(ours.TSDFFuser.__init__)[:5] == params(ref.TSDFFuser.__init__)
+    assert params(ours.get_frustum_bounds) == params(ref.get_frustum_bounds)
+    assert ours.TSDF.VOX_MOD == ref.TSDF.VOX_MOD
+    f = ours.TSDFFuser(ours.TSDF.from_bounds(dict(xmin=0, xmax=0.4, ymin=0, ymax=0.4, zmin=0, zmax=0.4), 0.05))
+    rf = ref.TSDFFuser(ref.TSDF.from_bounds(dict(xmin=0, xmax=0.4, ymin=0, ymax=0.4, zmin=0, zmax=0.4), 0.05), use_gpu=False)
+    assert (f.truncation, f.maxW, f.min_depth, f.max_depth, tuple(f.shape)) == \
+           (rf.truncation, rf.maxW, rf.min_depth, rf.max_depth, tuple(rf.shape))
