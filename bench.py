@@ -386,6 +386,12 @@ def kernel_rooflines(model, dev_sets, cfg, flush, L, reps=5):
             "ms_per_launch": round(conv_ms / n_conv, 5), "launches_per_step": n_conv, "ms_all_launches": round(conv_ms, 4),
             "algorithmic_flops": conv_flops, "peak_source": peaks["src"] + " bf16 sustained"},
     }
+    if model.math == "tc3x":
+        # context for `frac`: an fp32-accurate tensor-core path issues 3 TF32 MMAs per product and TF32 runs at half the
+        # bf16 rate, so its ceiling is peak / 6 -- reported next to the contract's frac-of-bf16-peak, never instead of it
+        for e in entries.values():
+            e["ceiling_3xtf32"] = round(tens_peak / 6.0, 1)
+            e["frac_of_3xtf32_ceiling"] = round(e["achieved"] / (tens_peak / 6.0), 4)
     dom = "conv_stack" if conv_ms >= cv_ms else "cost_volume_mlp_hint"
     d = dict(entries[dom])
     d["kernel"] = dom
