@@ -18,7 +18,7 @@
 namespace dtb200 {
 
 uint64_t conv_tc_workspace_bytes(const dtb200_conv_params& p, int in_c_total);  // conv_tc.cu
-void conv_tc_init();                                                            // conv_tc.cu
+int conv_tc_init();                                                             // conv_tc.cu
 
 namespace {
 

@@ -13,6 +13,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "tc_common.cuh"
@@ -1088,27 +1090,32 @@ static TensorMapEncodeFn tensor_map_encoder() {
   return fn;
 }
 
-// One-time host state (driver entry point, SM count, opt-in shared memory) resolved outside any stream capture.
-static int g_num_sms = 0;
-void conv_tc_init() {
-  static bool done = false;
-  if (done) return;
-  tensor_map_encoder();
+// Per-device host state (SM count, opt-in shared memory), resolved on first use of each device outside any stream capture.
+// cudaFuncSetAttribute is per device, so a process that drives several GPUs initialises each of them; the once-flags make
+// concurrent first calls from several host threads safe.
+static int g_num_sms_dev[64] = {0};
+static std::once_flag g_init_once[64];
+int conv_tc_init() {
   int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  if (g_num_sms <= 0) g_num_sms = 148;
-  cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, false>::kSmemBytes);
-  cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, false>::kSmemBytes);
-  cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, true>::kSmemBytes);
-  cudaFuncSetAttribute(conv_tc_kernel<64, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true, 2>::kSmemBytes);
-  cudaFuncSetAttribute(conv_tc_kernel<64, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true, 3>::kSmemBytes);
-  cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true>::kSmemBytes);
-  cudaFuncSetAttribute(conv_tc_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64, 1>::kSmemBytes);
-  cudaFuncSetAttribute(conv_tc_halo_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64, 3>::kSmemBytes);
-  cudaFuncSetAttribute(conv_tc_halo_tail_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64, 3>::kSmemBytes);
-  cudaGetLastError();
-  done = true;
+  if (dev < 0 || dev >= 64) dev = 0;
+  std::call_once(g_init_once[dev], [dev] {
+    tensor_map_encoder();
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms_dev[dev] = sms > 0 ? sms : 148;
+    cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, false>::kSmemBytes);
+    cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, false>::kSmemBytes);
+    cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, true>::kSmemBytes);
+    cudaFuncSetAttribute(conv_tc_kernel<64, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true, 2>::kSmemBytes);
+    cudaFuncSetAttribute(conv_tc_kernel<64, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true, 3>::kSmemBytes);
+    cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true>::kSmemBytes);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64, 1>::kSmemBytes);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64, 3>::kSmemBytes);
+    cudaFuncSetAttribute(conv_tc_halo_tail_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64, 3>::kSmemBytes);
+    cudaGetLastError();
+  });
+  return g_num_sms_dev[dev];
 }
 
 // split-K plan for maps with fewer (M, N) tiles than SMs.  The kernel is persistent, so time ~ rounds x (K blocks per
@@ -1302,7 +1309,7 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(DTB200_ERR_CUDA, "conv (tc3x halo): cuTensorMapEncodeTiled failed with code %s%lld", "", (long long)r);
       }
-      conv_tc_init();
+      const int g_num_sms = conv_tc_init();
       const unsigned hgrid = (unsigned)(hw.total < g_num_sms ? hw.total : g_num_sms);
       HaloTailWork tw;
       int tail_tiles = 0;
@@ -1340,8 +1347,7 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DTB200_ERR_CUDA, "conv (tc3x): cuTensorMapEncodeTiled failed with code %s%lld", "", (long long)r);
   }
-  conv_tc_init();
-  const int num_sms = g_num_sms;
+  const int num_sms = conv_tc_init();
   const unsigned grid = (unsigned)(wk.total < num_sms ? wk.total : num_sms);
   const int dbg = conv_flags() >> 8;  // timing knock-outs (results are wrong): 1 no MMA, 2 no split, 4 no A box, 8 no B tile, 16 no store
   if (bn == 128 && !(conv_flags() & 2)) {

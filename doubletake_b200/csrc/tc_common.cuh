@@ -1,6 +1,7 @@
 // sm_100a tensor-core plumbing shared by the tcgen05 kernels: mbarrier, bulk async copy, TMEM alloc/ld, UMMA descriptors,
 // the 3xTF32 operand split.  Inline PTX only (no CUTLASS); the bit layouts follow cute/arch/mma_sm100_desc.hpp.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -181,6 +182,45 @@ __host__ __device__ __forceinline__ float tf32_big(float x) {
   v.u &= 0xFFFFE000u;
   return v.f;
 #endif
+}
+
+
+// ---------------------------------------------------------------------------------------------- 2-term fp16 split (TCH)
+// x = big + small' / 2048 with big = fp16(x) (round to nearest) and small' = fp16((x - big) * 2048): 22 significant bits,
+// |x - (big + small'/2048)| <= 2^-22 |x| for |x| in the fp16 range (denormals of both terms keep the ABSOLUTE error below
+// 2^-36).  a*b ~= big_a*big_b + (big_a*small'_b + small'_a*big_b) / 2048: three kind::f16 MMAs (twice the TF32 rate, half
+// the operand bytes of 3xTF32), the two correction products accumulate in their own TMEM columns and are scaled in the
+// epilogue.  Values are clamped to the finite fp16 range first (inf * 0 inside an MMA would poison whole rows).
+constexpr float kHalfSplitScale = 2048.f;
+constexpr float kHalfSplitInv = 1.f / 2048.f;
+constexpr float kHalfMax = 65504.f;
+
+__device__ __forceinline__ void split_half2(float x0, float x1, uint32_t& big, uint32_t& small) {
+  x0 = fminf(fmaxf(x0, -kHalfMax), kHalfMax);  // NaN stays NaN (fminf/fmaxf return the non-NaN operand: clamp maps NaN to
+  x1 = fminf(fmaxf(x1, -kHalfMax), kHalfMax);  // -65504; callers that must keep NaN handle it before the split)
+  const __half2 b = __floats2half2_rn(x0, x1);
+  const float2 bf = __half22float2(b);
+  const __half2 s = __floats2half2_rn((x0 - bf.x) * kHalfSplitScale, (x1 - bf.y) * kHalfSplitScale);
+  big = *reinterpret_cast<const uint32_t*>(&b);
+  small = *reinterpret_cast<const uint32_t*>(&s);
+}
+__device__ __forceinline__ float join_half(__half b, __half s) { return fmaf(__half2float(s), kHalfSplitInv, __half2float(b)); }
+
+// byte offset of element (row, k) inside a [rows][64 fp16] SWIZZLE_128B K-major tile
+__host__ __device__ __forceinline__ uint32_t sw128_offset_h(int row, int k) {
+  return (uint32_t)row * 128u + (uint32_t)((((k >> 3) ^ (row & 7)) << 4) + ((k & 7) << 1));
+}
+// Instruction descriptor, kind::f16 with fp16 A/B (format 0), fp32 accumulate, A and B K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
 }
 
 }  // namespace tc

@@ -107,13 +107,11 @@ class DepthModelCVHint(nn.Module):
         return cur, src
 
     # -------------------------------------------------------------------------------------- host -> device staging
-    _EARLY_KEYS = ("cam_T_world_b44", "world_T_cam_b44", "matching_feats_bchw", "matching_feats_bkchw",
-                   "depth_hint_b1hw", "sampled_weights_b1hw", "depth_hint_mask_b1hw", "image_b3hw")
-
     def _upload(self, cur_data, src_data, dev):
         """Inputs that still live in HOST memory (the reference moves the whole batch with ``to_gpu`` before forward,
         utils/generic_utils.py) are copied on a dedicated copy stream in the order the kernels need them: poses,
-        intrinsics, matching features and hint first (the cost volume waits on event 0), the image-prior feature maps
+        intrinsics, matching features and hint first (the cost volume waits on event 0; EVERY non-list tensor is in this
+        group, so no kernel can read an input whose copy it did not wait for), the list-valued image-prior feature maps
         last (only the conv plan waits on event 1).  With pinned buffers the copies of frame i+1 overlap the kernels of
         frame i, and a frame's prior maps travel while its cost volume is being computed.
         Returns (cur_data, src_data, (event_early, event_late)) -- events are None when nothing had to move."""
@@ -147,10 +145,8 @@ class DepthModelCVHint(nn.Module):
                 for k, v in d.items():
                     if isinstance(v, (list, tuple)):
                         late.append((o, k, v))
-                    elif k in self._EARLY_KEYS or (torch.is_tensor(v) and v.numel() <= 4096):
-                        o[k] = move(v)
                     else:
-                        late.append((o, k, v))
+                        o[k] = move(v)  # every plain tensor is "early": only the list-valued prior maps travel late
             ev_early = copy.record_event()
             for o, k, v in late:
                 o[k] = [move(x) for x in v] if isinstance(v, (list, tuple)) else move(v)
@@ -177,7 +173,7 @@ class DepthModelCVHint(nn.Module):
 
     def _network_plan(self, cv_shape, prior_feats):
         key = (tuple(cv_shape), tuple(tuple(f.shape) for f in prior_feats), self.math)
-        if key not in self._plans:
+        if key not in self._plans or self._plans[key].stale():
             ms = self.run_opts.matching_scale
             plan = ConvPlan(prior_feats[0].device, self.math)
             fcv = plan.input("cv", *cv_shape)

@@ -45,6 +45,7 @@ class ConvPlan:
         self.keep = []  # tensors referenced by raw pointers
         self.inputs = {}  # name -> Feature filled from an NCHW tensor before run()
         self._packed = {}
+        self._tracked = []  # (parameter, version at pack time): stale() tells the owner to rebuild the plan
         self._upsampled = {}
         self._array = None
         self.workspace = None
@@ -66,8 +67,9 @@ class ConvPlan:
 
     def _pack(self, weight, src_channels):
         """Device copy of an OIHW weight in the layout the math mode consumes, for this concat split of its inputs."""
-        key = (weight.data_ptr(), tuple(src_channels))
+        key = (weight.data_ptr(), weight._version, tuple(src_channels))
         if key not in self._packed:
+            self._tracked.append((weight, weight._version))
             w = L.f32(weight.detach(), self.device)
             oc, ic, k, _ = w.shape
             split = (C.c_int32 * len(src_channels))(*src_channels)
@@ -124,8 +126,10 @@ class ConvPlan:
             raise ValueError(f"conv expects {conv.in_channels} input channels, sources provide {total_c}")
         op.weight = L.ptr(self._pack(conv.weight, [f.c for f, _ in srcs]))
         if conv.bias is not None:
-            bias = L.f32(conv.bias.detach(), self.device)
+            # snapshot, like the packed weights: a plan never mixes stale weights with live biases
+            bias = L.f32(conv.bias.detach(), self.device).clone()
             self.keep.append(bias)
+            self._tracked.append((conv.bias, conv.bias._version))
             op.bias = L.ptr(bias)
         out = self.new(f0.b, out_h, out_w, conv.out_channels)
         if residual is not None:
@@ -152,6 +156,11 @@ class ConvPlan:
                 self.ops[i].workspace, self.ops[i].workspace_bytes = base + (n % slots) * need, need
         self._array = (L.ConvParams * len(self.ops))(*self.ops)
         return self
+
+    def stale(self):
+        """True when a parameter this plan snapshot (packed weights, bias copies) was modified in place afterwards
+        (``param.data.copy_``, EMA, a fine-tune step): the owner rebuilds the plan instead of running stale weights."""
+        return any(t._version != v for t, v in self._tracked)
 
     def analyze(self):
         """Host-side dependency analysis of the plan (no launch): per-op lane, level and direct dependencies."""
@@ -194,6 +203,10 @@ class ConvPlan:
             if not x.is_cuda:
                 raise RuntimeError("doubletake_b200 networks run on CUDA only (no CPU fallback)")
             L.nchw_to_nhwc(x, out=f.t)
+
+    def output_nchw(self, f):
+        """A plan buffer as a fresh NCHW fp32 tensor (what the reference-facing ``forward`` methods return)."""
+        return _nchw_out(f)
 
     def run(self):
         if self.mode != "graph":
@@ -268,7 +281,7 @@ class _PlannedModule(nn.Module):
 
     def _plan_for(self, key, build):
         key = (key, self.math)
-        if key not in self._plans:
+        if key not in self._plans or self._plans[key].stale():
             self._plans[key] = build()
         return self._plans[key]
 

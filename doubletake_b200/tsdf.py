@@ -9,8 +9,9 @@ as the reference's fp16 tensors; ``integrate_depth`` is ONE CUDA kernel per batc
 Mesh extraction (``to_mesh*``, marching cubes) is row N3 and not part of this engine yet.
 
 Numerics: the kernels reproduce the reference's fp16 torch ops rounding for rounding.  fp16 ``grid_sample`` behaves
-differently in ATen's CPU and CUDA builds (index arithmetic precision, non-finite indices); ``semantics="aten_cpu"``
-(default) is what the golden fixtures pin (the reference executed on CPU), ``"aten_cuda"`` follows GridSampler.cuh.
+differently in ATen's CPU and CUDA builds (index arithmetic precision, non-finite indices); ``semantics="aten_cuda"``
+(default: the reference fuser runs on CUDA) follows GridSampler.cuh and is pinned against torch's own CUDA ops on the GPU
+box (tests/test_gpu_tsdf.py), ``"aten_cpu"`` is what the CPU-generated golden fixtures pin.
 ``sample_tsdf`` follows the reference's fp32 branch (its CUDA branch rounds the coordinates to fp16 first).
 """
 from __future__ import annotations
@@ -166,10 +167,21 @@ class TSDF:
         return out
 
 
+def _host_half(x):
+    """(B,4,4) poses / intrinsics as a host fp16 array.  numpy arrays and CPU tensors are used as they are (no device
+    synchronisation: the incremental loop keeps poses on the host); a CUDA tensor costs one blocking copy."""
+    if isinstance(x, np.ndarray):
+        return x.astype(np.float16)
+    return x.detach().to("cpu").half().numpy()
+
+
 class TSDFFuser:
     """reference ``TSDFFuser`` (tools/tsdf.py:340-558)."""
 
-    def __init__(self, tsdf, min_depth=0.5, max_depth=5.0, use_gpu=True, semantics="aten_cpu"):
+    def __init__(self, tsdf, min_depth=0.5, max_depth=5.0, use_gpu=True, semantics="aten_cuda"):
+        """``semantics`` selects which ATen build's fp16 ``grid_sample`` is reproduced: "aten_cuda" (default -- the
+        reference fuser always runs with use_gpu=True, tools/fusers_helper.py) or "aten_cpu" (what fixtures generated by
+        executing the reference on a CPU-only machine pin; differs only for non-finite / overflowing pixel coordinates)."""
         if not use_gpu:
             raise RuntimeError("doubletake_b200 runs on CUDA only (no CPU fallback): use_gpu must be True")
         if semantics not in L.TSDF_SEMANTICS:
@@ -201,16 +213,23 @@ class TSDFFuser:
         P = _matmul_h_np(K, T)[:3]
         return P.astype(np.float32).ravel().tolist(), lo.astype(np.float32).tolist(), hi.astype(np.float32).tolist()
 
-    def _index_box(self, lo, hi, dims, margin=2):
-        """Conservative index cover [begin, end) of the voxels whose fp16 coordinate can lie strictly inside (lo, hi):
-        coordinates grow monotonically with the index and fp16 rounding moves them by far less than ``margin`` voxels.
-        Caller-supplied grids (TSDF.from_file) and non-finite boxes scan the whole volume; z bounds are multiples of 8."""
+    def _index_box(self, lo, hi, dims):
+        """Conservative index cover [begin, end) of the voxels whose fp16 coordinate can lie strictly inside (lo, hi).
+        Coordinates grow monotonically with the index, but the stored coordinate is ROUNDED to fp16: far from the origin one
+        fp16 ulp spans several voxels (0.125 m at |x| >= 128 with 4 cm voxels), so the margin is derived from the ulp at the
+        largest coordinate magnitude of the axis.  Caller-supplied grids (TSDF.from_file), non-finite boxes and volumes
+        whose ulp exceeds 16 voxels scan the whole volume; z bounds are multiples of 8."""
         full = [0, 0, 0], list(dims)
         if self.tsdf._origin_f32 is None or not all(np.isfinite(lo + hi)):
             return full
         begin, end = [], []
         for a in range(3):
             o, vs = float(self.tsdf._origin_f32[a]), float(self.voxel_size)
+            reach = max(abs(o), abs(o + dims[a] * vs), abs(lo[a]), abs(hi[a]), 6.2e-5)
+            ulp = 2.0 ** (int(np.floor(np.log2(reach))) - 10)  # fp16 spacing at that magnitude
+            margin = int(np.ceil(ulp / vs)) + 2
+            if margin > 18:
+                return full
             b = int(np.floor((lo[a] - o) / vs)) - margin
             e = int(np.ceil((hi[a] - o) / vs)) + margin + 1
             begin.append(min(max(b, 0), dims[a]))
@@ -229,7 +248,7 @@ class TSDFFuser:
         depth = depth_b1hw.to(dev).half().contiguous()
         mask = None if depth_mask_b1hw is None else depth_mask_b1hw.to(dev).to(torch.uint8).contiguous()
         B, _, img_h, img_w = depth.shape
-        T_cpu, K_cpu = cam_T_world_T_b44.detach().cpu().half().numpy(), K_b44.detach().cpu().half().numpy()
+        T_cpu, K_cpu = _host_half(cam_T_world_T_b44), _host_half(K_b44)
         p = L.TsdfIntegrateParams()
         p.values, p.weights = L.ptr(values), L.ptr(weights)
         if self.tsdf._origin_f32 is not None:

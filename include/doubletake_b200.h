@@ -11,7 +11,8 @@
  *   - every pointer is a DEVICE pointer to fp32 unless stated; all tensors dense/contiguous in the stated layout
  *   - every entry point enqueues work on `stream` and returns immediately (0 = ok, <0 = error code below;
  *     dtb200_last_error() gives the message for the calling thread)
- *   - thread-safe per stream; no global mutable state besides the per-thread error string
+ *   - thread-safe per stream; process-global state is limited to the per-thread error string, the launch counter, per-device
+ *     one-time kernel attributes (std::call_once) and the development switches of dtb200_debug_set
  */
 #ifndef DOUBLETAKE_B200_H
 #define DOUBLETAKE_B200_H

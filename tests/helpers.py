@@ -84,3 +84,14 @@ def network_case_inputs(fx, decoder):
     g = torch.Generator().manual_seed(seed + 11)
     cv = torch.randn(B, D, ih // 4, iw // 4, generator=g)
     return cfg, cv, priors, seed
+
+
+def log_argmax(tag, n_bad, n_total, extra=""):
+    """One line per parity case with the arg-max mismatch COUNT (record it, do not hide it behind an allowance):
+    printed (pytest -s / -rP shows it) and appended to gpurun_out/argmax_mismatch.log when that directory exists."""
+    line = f"[argmax] {tag}: {n_bad} of {n_total} pixels differ from the reference arg-max {extra}".rstrip()
+    print(line)
+    out = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "argmax_mismatch.log"), "a") as f:
+            f.write(line + "\n")

@@ -76,7 +76,7 @@ def test_more_frames_than_one_launch_holds():
     K = np.concatenate([fx["K"], fx["K"]], 0)
     assert depth.shape[0] > L.TSDF_MAX_FRAMES
     vol = bt.TSDF.from_bounds(case_bounds(fx), float(fx["voxel_size"]))
-    bt.TSDFFuser(vol, max_depth=float(fx["max_depth"])).integrate_depth(
+    bt.TSDFFuser(vol, max_depth=float(fx["max_depth"]), semantics="aten_cpu").integrate_depth(
         torch.from_numpy(depth.copy()).cuda(), torch.from_numpy(T.copy()), torch.from_numpy(K.copy()))
     ref = ot.volume_from_bounds(case_bounds(fx), float(fx["voxel_size"]))
     ot.integrate_depth(ref, depth, T, K, min_depth=0.5, max_depth=float(fx["max_depth"]))
@@ -93,6 +93,36 @@ def test_aten_cuda_semantics_match_their_restatement():
     assert np.array_equal(bits(vol.tsdf_values), bits(ref["tsdf_values"]))
     assert np.array_equal(bits(vol.tsdf_weights), bits(ref["tsdf_weights"]))
     assert not np.array_equal(bits(vol.tsdf_weights), bits(fx["weights"]))  # the pinned build differs on overflowed pixels
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_aten_cuda_semantics_match_torch_cuda_ops(name):
+    """pin the DEFAULT (aten_cuda) branch against ATen's own CUDA kernels.  oracle_tsdf_torch.integrate_depth is
+    the reference's op sequence (bit-exact against the fixtures on the CPU, tests/test_oracle_tsdf_golden.py); here it
+    runs on the GPU, where torch's CUDA grid_sample / fp16 elementwise kernels / cuBLAS decide every rounding.
+    cuBLAS evaluates the (3x4)@(4xN) fp16 projection with its own accumulation order, which may flip an fp16 rounding on
+    a handful of voxels (and then, through the nearest-pixel lookup, their sampled depth): the bar is >= 99.9 % of the
+    touched voxels bit-identical, the count is printed."""
+    from oracle import oracle_tsdf_torch as ott
+
+    fx = hp.load(name)
+    seed, nf, ih, iw, fb, with_mask, ext = [int(v) for v in fx["meta"]]
+    vol, _ = run_case(fx, semantics="aten_cuda")
+    coords = torch.from_numpy(fx["voxel_coords"]).cuda()
+    values = -torch.ones(coords.shape[1:], dtype=torch.float16, device="cuda")
+    weights = torch.zeros(coords.shape[1:], dtype=torch.float16, device="cuda")
+    for s in range(0, nf, fb):
+        ott.integrate_depth(coords, values, weights, float(fx["voxel_size"]), torch.from_numpy(fx["depth"][s:s + fb]).cuda(),
+                            torch.from_numpy(fx["cam_T_world"][s:s + fb]).cuda(), torch.from_numpy(fx["K"][s:s + fb]).cuda(),
+                            min_depth=0.5, max_depth=float(fx["max_depth"]),
+                            depth_mask_b1hw=torch.from_numpy(fx["mask"][s:s + fb]).cuda() if with_mask else None,
+                            extended_neg_truncation=bool(ext))
+    torch.cuda.synchronize()
+    touched = int((weights > 0).sum())
+    dv = int((bits(vol.tsdf_values) != bits(values)).sum())
+    dw = int((bits(vol.tsdf_weights) != bits(weights)).sum())
+    print(f"[tsdf aten_cuda vs torch CUDA] {name}: touched {touched}, value bits differ {dv}, weight bits differ {dw}")
+    assert touched > 10000 and dv <= touched // 1000 and dw <= touched // 1000, (touched, dv, dw)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -117,7 +147,7 @@ def test_reference_default_volume_lazy_grid():
     fx = hp.load("tsdf_room")
     big = bt.TSDF.from_bounds(dict(xmin=-10.0, xmax=10.0, ymin=-10.0, ymax=10.0, zmin=-10.0, zmax=10.0), 0.04, lazy_grid=True)
     assert tuple(big.tsdf_values.shape) == (504, 504, 504)
-    fuser = bt.TSDFFuser(big, max_depth=float(fx["max_depth"]))
+    fuser = bt.TSDFFuser(big, max_depth=float(fx["max_depth"]), semantics="aten_cpu")
     depth, T, K = (torch.from_numpy(fx[k]) for k in ("depth", "cam_T_world", "K"))
     fuser.integrate_depth(depth[:2].cuda(), T[:2], K[:2])
     torch.cuda.synchronize()

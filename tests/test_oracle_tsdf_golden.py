@@ -73,7 +73,7 @@ def test_host_mirror_grid_and_frame_constants(name):
     assert np.array_equal(bits(vol.voxel_coords_3hwd.numpy()), bits(fx["voxel_coords"]))
     assert np.array_equal(bits(vol.origin.numpy()), bits(fx["origin"]))
     assert tuple(vol.tsdf_values.shape) == fx["values"].shape and float(vol.tsdf_values.float().max()) == -1.0
-    fuser = bt.TSDFFuser(vol, max_depth=float(fx["max_depth"]))
+    fuser = bt.TSDFFuser(vol, max_depth=float(fx["max_depth"]), semantics="aten_cpu")
     ih, iw = fx["depth"].shape[2:]
     for b in range(fx["depth"].shape[0]):
         K, T = torch.from_numpy(fx["K"][b]), torch.from_numpy(fx["cam_T_world"][b])
@@ -110,7 +110,7 @@ def test_index_box_covers_every_voxel_of_the_frustum_box(name):
     strict box test (and stay well below the whole volume for a camera inside a large one)."""
     fx = hp.load(name)
     vol = bt.TSDF.from_bounds(case_bounds(fx), float(fx["voxel_size"]))
-    fuser = bt.TSDFFuser(vol, max_depth=float(fx["max_depth"]))
+    fuser = bt.TSDFFuser(vol, max_depth=float(fx["max_depth"]), semantics="aten_cpu")
     ih, iw = fx["depth"].shape[2:]
     c = fx["voxel_coords"].astype(np.float32)
     dims = c.shape[1:]
@@ -126,7 +126,51 @@ def test_index_box_covers_every_voxel_of_the_frustum_box(name):
         assert all(idx[:, a].min() >= begin[a] and idx[:, a].max() < end[a] for a in range(3))
     big = bt.TSDF(None, torch.zeros(8, 8, 8), torch.zeros(8, 8, 8), 0.04, torch.tensor([-10.0, -10.0, -10.0]),
                   _origin_f32=torch.tensor([-10.0, -10.0, -10.0]))
-    bf = bt.TSDFFuser(big, max_depth=3.0)
+    bf = bt.TSDFFuser(big, max_depth=3.0, semantics="aten_cpu")
     begin, end = bf._index_box(lo, hi, (504, 504, 504))
     assert np.prod([e - b for b, e in zip(begin, end)]) < 0.05 * 504 ** 3
     assert bf._index_box([float("nan")] * 3, hi, (504, 504, 504)) == ([0, 0, 0], [504, 504, 504])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_torch_restatement_is_bit_exact_on_cpu(name):
+    """oracle/oracle_tsdf_torch.py executes the reference's torch ops in the reference's order; on the CPU it must land on
+    the fixtures bit for bit.  The GPU suite then runs the SAME function on CUDA to pin the product's aten_cuda branch."""
+    from oracle import oracle_tsdf_torch as ott
+
+    fx = hp.load(name)
+    seed, nf, ih, iw, batch, with_mask, ext = [int(v) for v in fx["meta"]]
+    coords = torch.from_numpy(fx["voxel_coords"])
+    values = -torch.ones(coords.shape[1:], dtype=torch.float16)
+    weights = torch.zeros(coords.shape[1:], dtype=torch.float16)
+    for s in range(0, nf, batch):
+        ott.integrate_depth(coords, values, weights, float(fx["voxel_size"]), torch.from_numpy(fx["depth"][s:s + batch]),
+                            torch.from_numpy(fx["cam_T_world"][s:s + batch]), torch.from_numpy(fx["K"][s:s + batch]),
+                            min_depth=float(fx["min_depth"]), max_depth=float(fx["max_depth"]),
+                            depth_mask_b1hw=torch.from_numpy(fx["mask"][s:s + batch]) if with_mask else None,
+                            extended_neg_truncation=bool(ext))
+    assert np.array_equal(bits(values.numpy()), bits(fx["values"]))
+    assert np.array_equal(bits(weights.numpy()), bits(fx["weights"]))
+
+
+def test_index_box_margin_follows_the_fp16_ulp_far_from_the_origin():
+    """at |coord| >= 128 one fp16 ulp is 0.125 m = 3 voxels of 4 cm; the scanned index box must still contain
+    every voxel whose ROUNDED coordinate passes the strict box test."""
+    origin = np.array([250.0, -300.0, 120.0], np.float32)
+    dims = (64, 64, 64)
+    vs = 0.04
+    vol = bt.TSDF(None, torch.zeros(dims), torch.zeros(dims), vs, torch.from_numpy(origin).half(),
+                  _origin_f32=torch.from_numpy(origin))
+    fuser = bt.TSDFFuser(vol, max_depth=3.0)
+    coords = ot.generate_voxel_coords(origin, dims, vs).astype(np.float32)
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        lo = (origin + rng.uniform(0.2, 1.0, 3)).astype(np.float16).astype(np.float32)
+        hi = (lo + rng.uniform(0.3, 1.2, 3)).astype(np.float16).astype(np.float32)
+        begin, end = fuser._index_box(lo.tolist(), hi.tolist(), dims)
+        inside = np.ones(dims, bool)
+        for a in range(3):
+            inside &= (coords[a] > lo[a]) & (coords[a] < hi[a])
+        idx = np.argwhere(inside)
+        if len(idx):
+            assert all(idx[:, a].min() >= begin[a] and idx[:, a].max() < end[a] for a in range(3)), (lo, hi, begin, end)

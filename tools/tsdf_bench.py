@@ -34,7 +34,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for nb in (1, 6):
         vol = bt.TSDF.from_bounds(dict(xmin=-10.0, xmax=10.0, ymin=-10.0, ymax=10.0, zmin=-10.0, zmax=10.0), 0.04, lazy_grid=True)
-        fuser = bt.TSDFFuser(vol, max_depth=3.0)
+        fuser = bt.TSDFFuser(vol, max_depth=3.0, semantics="aten_cpu")
         fuser.integrate_depth(depth[:nb], T[:nb], K[:nb])
         torch.cuda.synchronize()
         touched = int((vol.tsdf_weights > 0).sum())
