@@ -51,7 +51,6 @@ struct TcCfg {
 //   bit 0: issue the 64-channel tiles as three N=64 MMAs per K step instead of the merged N=128 + N=64 pair
 //   bit 1: same for the 128-channel tiles (their merged form, N=256 + N=128, takes all 512 TMEM columns)
 //   bit 2: previous split-K rule (many short items) instead of the round-count cost model
-//   bit 4: halo kernel with the last partial persistent round split along K (conv_tc_halo_tail_kernel; not yet GPU-validated)
 //   bit 7: no halo-tile kernel (3x3 / stride-1 layers use the tap-major kernel too); bit 3: halo kernel with 1 tap per
 //          weight-ring stage instead of 3
 //   bits 8..12: timing knock-outs of the tensor-core conv pipeline (results are WRONG; tools/conv_bench.py --debug)
@@ -701,319 +700,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const dtb200_
   }
 }
 
-// ----------------------------------------------------------------------------------------------------------------------
-// Halo kernel with a split tail round (development switch, bit 4 of the flags; NOT yet validated on a GPU).
-//
-// A persistent kernel with T tiles on 148 SMs runs ceil(T / 148) rounds; 600 tiles (240x320) are 4.05 rounds of work that
-// cost 5, 160 tiles (120x160) 1.08 that cost 2.  Here the T mod 148 tiles of the last, partial round are cut along K into
-// `parts` pieces of `upp` units each (unit = one weight-ring stage = 3 taps of one 32-channel chunk), so that the tail round
-// holds <= 148 short items instead of a few full ones.  Partial items write raw fp32 accumulators to a workspace
-// [tail tile][part][128 rows][BN]; halo_tail_reduce_kernel sums the parts in order (deterministic) and applies bias /
-// residual / activation.  Full items behave exactly like conv_tc_halo_kernel<BN, 3>.
-struct HaloTailWork {
-  int full_items;  // tiles [0, full_items) are whole items; item full_items + j is part (j % parts) of tile full_items + j / parts
-  int parts, upp, units;  // units = 3 * chunks
-  long long total_items;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_tail_kernel(const dtb200_conv_params p, const __grid_constant__ TcMaps maps,
-                                                                        KLayout kl, TcWork wk, HaloTailWork tw,
-                                                                        float* __restrict__ partial) {
-  constexpr int kTB = 3;
-  using Cfg = HaloCfg<BN, kTB>;
-  constexpr int SA = kHaloAStages, SB = Cfg::kBStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* ring_a = smem;
-  uint8_t* ring_b = ring_a + SA * kHaloAStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_b + SB * Cfg::kBStageBytes);
-  uint64_t* raw_full = bars;
-  uint64_t* a_full = raw_full + SA;
-  uint64_t* a_empty = a_full + SA;
-  uint64_t* b_full = a_empty + SA;
-  uint64_t* b_empty = b_full + SB;
-  uint64_t* acc_full = b_empty + SB;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    for (int s = 0; s < SA; ++s) mbar_init(&raw_full[s], 1), mbar_init(&a_full[s], kSplitWarps), mbar_init(&a_empty[s], 1);
-    for (int s = 0; s < SB; ++s) mbar_init(&b_full[s], 1), mbar_init(&b_empty[s], 1);
-    for (int s = 0; s < 2; ++s) mbar_init(&acc_full[s], 1), mbar_init(&acc_empty[s], kEpilogueWarps);
-    fence_mbar_init();
-  }
-  if (warp == kMmaWarp) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int chunks = kl.kb_per_tap;
-
-  // item -> tile, unit range [u0, u1) and part (-1 = whole tile).  Every role walks the same ranges.
-  auto decode = [&](long long item, int& bb, int& y0, int& x0, int& n_tile, int& u0, int& u1, int& part, int& tail_tile) {
-    long long tile;
-    if (item < tw.full_items) {
-      tile = item, u0 = 0, u1 = tw.units, part = -1, tail_tile = 0;
-    } else {
-      const long long j = item - tw.full_items;
-      tail_tile = (int)(j / tw.parts);
-      part = (int)(j - (long long)tail_tile * tw.parts);
-      tile = tw.full_items + tail_tile;
-      u0 = part * tw.upp;
-      u1 = min(tw.units, u0 + tw.upp);
-    }
-    n_tile = (int)(tile % wk.n_tiles);
-    const int m_tile = (int)(tile / wk.n_tiles);
-    const int per_img = wk.tiles_x * wk.tiles_y;
-    bb = m_tile / per_img;
-    const int t = m_tile - bb * per_img;
-    y0 = (t / wk.tiles_x) * kHaloTH;
-    x0 = (t % wk.tiles_x) * kHaloTW;
-  };
-
-  if (warp < kEpilogueWarps) {
-    // ============================================================ epilogue
-    const int row = warp * 32 + lane;
-    const int ty = row / kHaloTW, tx = row - ty * kHaloTW;
-    int use = 0;
-    for (long long item = blockIdx.x; item < tw.total_items; item += gridDim.x, ++use) {
-      int bb, y0, x0, n_tile, u0, u1, part, tail_tile;
-      decode(item, bb, y0, x0, n_tile, u0, u1, part, tail_tile);
-      const int buf = use & 1;
-      const int oy = y0 + ty, ox = x0 + tx;
-      const bool live = oy < p.out_h && ox < p.out_w;
-      const long long m = ((long long)bb * p.out_h + oy) * p.out_w + ox;
-      const int n_base = n_tile * BN;
-      float* dst = p.dst + m * p.out_c + n_base;
-      const float* res = p.residual ? p.residual + m * p.out_c + n_base : nullptr;
-      float* pdst = partial + (((size_t)tail_tile * tw.parts + (size_t)max(part, 0)) * kBM + row) * BN;
-      mbar_wait(&acc_full[buf], (use >> 1) & 1, 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(buf * Cfg::kAccCols) + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-      for (int cc = 0; cc < BN; cc += 32) {
-        float r[32];
-        const bool use_res = res != nullptr && live && part < 0;
-        if (use_res) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) ldg256(res + cc + j, r + j);
-        }
-        float v[32], v2[32];
-        tmem_ld32(taddr + (uint32_t)cc, v);
-        tmem_ld32(taddr + (uint32_t)(BN + cc), v2);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += v2[j];
-        if (part >= 0) {  // raw partial sums of this K range; bias / residual / activation happen in the reduce kernel
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) stg256(pdst + cc + j, v + j);
-          continue;
-        }
-        if (!live) continue;
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bv = ld4(p.bias + n_base + cc + j);
-            v[j] += bv.x, v[j + 1] += bv.y, v[j + 2] += bv.z, v[j + 3] += bv.w;
-          }
-        }
-        if (use_res) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += r[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.act, p.act_slope);
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) stg256(dst + cc + j, v + j);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
-    }
-  } else if (warp < kMmaWarp) {
-    // ============================================================ splitters
-    const int st = tid - kEpilogueWarps * 32;
-    constexpr int kUnits = kHaloPatchBytes / 16;
-    const uint32_t ring_u = smem_u32(ring_a);
-    int stage = 0, phase = 0;
-    for (long long item = blockIdx.x; item < tw.total_items; item += gridDim.x) {
-      int bb, y0, x0, n_tile, u0, u1, part, tail_tile;
-      decode(item, bb, y0, x0, n_tile, u0, u1, part, tail_tile);
-      const int ch_begin = u0 / 3, ch_last = (u1 - 1) / 3;
-#pragma unroll 1
-      for (int ch = ch_begin; ch <= ch_last; ++ch) {
-        mbar_wait(&raw_full[stage], phase, 2);
-        const uint32_t raw_u = ring_u + (uint32_t)(stage * kHaloAStageBytes);
-        float4 v[12];
-#pragma unroll
-        for (int it = 0; it < 12; ++it) {
-          const int u = st + it * 128;
-          if (u < kUnits) v[it] = lds128(raw_u + (uint32_t)u * 16u);
-        }
-#pragma unroll
-        for (int it = 0; it < 12; ++it) {
-          const int u = st + it * 128;
-          if (u < kUnits) {
-            const float4 x = v[it];
-            const float4 big = make_float4(tf32_big(x.x), tf32_big(x.y), tf32_big(x.z), tf32_big(x.w));
-            sts128(raw_u + kHaloSlotBytes + (uint32_t)u * 16u, make_float4(x.x - big.x, x.y - big.y, x.z - big.z, x.w - big.w));
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[stage]);
-        if (++stage == SA) stage = 0, phase ^= 1;
-      }
-    }
-  } else if (warp == kMmaWarp) {
-    // ============================================================ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
-    constexpr uint32_t idesc2 = umma_idesc_tf32(kBM, 2 * BN);
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    constexpr uint32_t kDescHiA = (uint32_t)(kHaloPW * 128 / 16) | (1u << 14) | (2u << 29);
-    constexpr uint32_t kDescHiB = 64u | (1u << 14) | (2u << 29);
-    const uint32_t lo_ring_a = ((smem_u32(ring_a) & 0x3FFFFu) >> 4) | (1u << 16);
-    const uint32_t lo_ring_b = ((smem_u32(ring_b) & 0x3FFFFu) >> 4) | (1u << 16);
-    auto desc_a = [](uint32_t lo) { return ((uint64_t)kDescHiA << 32) | lo; };
-    auto desc_b = [](uint32_t lo) { return ((uint64_t)kDescHiB << 32) | lo; };
-    int sa = 0, pa = 0, sb = 0, pb = 0, use = 0;
-    for (long long item = blockIdx.x; item < tw.total_items; item += gridDim.x, ++use) {
-      int bb, y0, x0, n_tile, u0, u1, part, tail_tile;
-      decode(item, bb, y0, x0, n_tile, u0, u1, part, tail_tile);
-      const int ch_begin = u0 / 3, ch_last = (u1 - 1) / 3;
-      const int buf = use & 1;
-      mbar_wait(&acc_empty[buf], ((use >> 1) & 1) ^ 1, 3);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_u + (uint32_t)(buf * Cfg::kAccCols);
-      for (int ch = ch_begin; ch <= ch_last; ++ch) {
-        mbar_wait(&a_full[sa], pa, 4);
-        tc_fence_after();
-        const uint32_t lo_raw = lo_ring_a + (uint32_t)sa * (kHaloAStageBytes >> 4);
-        const uint32_t lo_small = lo_raw + (kHaloSlotBytes >> 4);
-        const int g_lo = (ch == ch_begin) ? u0 - ch * 3 : 0;
-        const int g_hi = (ch == ch_last) ? (u1 - 1) - ch * 3 : 2;
-#pragma unroll 1
-        for (int g = g_lo; g <= g_hi; ++g) {
-          mbar_wait(&b_full[sb], pb, 5);
-          tc_fence_after();
-          const uint32_t lo_b_stage = lo_ring_b + (uint32_t)sb * (Cfg::kBStageBytes >> 4);
-          const bool first_unit = (ch == ch_begin) && (g == g_lo);  // first MMA of the item overwrites the accumulator
-          if (elect_one()) {
-#pragma unroll
-            for (int t = 0; t < kTB; ++t) {
-              const int tap = g * kTB + t;
-              const int ky = tap / 3, kx = tap - ky * 3;
-              const uint32_t shift = (uint32_t)(ky * kHaloPW + kx) * (128u >> 4);
-              const uint32_t lo_b_big = lo_b_stage + (uint32_t)t * (Cfg::kBBytes >> 4);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t ko = ks * 2;
-                umma_tf32(tmem_d, desc_a(lo_raw + shift + ko), desc_b(lo_b_big + ko), idesc2, !(first_unit && t == 0 && ks == 0));
-                umma_tf32(tmem_d, desc_a(lo_small + shift + ko), desc_b(lo_b_big + ko), idesc, true);
-              }
-            }
-            umma_commit(&b_empty[sb]);
-            if (g == g_hi) umma_commit(&a_empty[sa]);
-          }
-          __syncwarp();
-          if (++sb == SB) sb = 0, pb ^= 1;
-        }
-        if (++sa == SA) sa = 0, pa ^= 1;
-      }
-      if (elect_one()) umma_commit(&acc_full[buf]);
-      __syncwarp();
-    }
-  } else if (warp == kLoadWarp) {
-    // ============================================================ A loader
-    int stage = 0, phase = 0;
-    for (long long item = blockIdx.x; item < tw.total_items; item += gridDim.x) {
-      int bb, y0, x0, n_tile, u0, u1, part, tail_tile;
-      decode(item, bb, y0, x0, n_tile, u0, u1, part, tail_tile);
-      const int ch_begin = u0 / 3, ch_last = (u1 - 1) / 3;
-      int src = 0, c0 = 0;
-      for (int i = 0; i < ch_begin; ++i) {  // (source, channel offset) of the item's first chunk
-        c0 += kBK;
-        if (c0 >= (src == 0 ? kl.src_c[0] : (src == 1 ? kl.src_c[1] : kl.src_c[2]))) c0 = 0, ++src;
-      }
-      for (int ch = ch_begin; ch <= ch_last; ++ch) {
-        mbar_wait(&a_empty[stage], phase ^ 1, 6);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&raw_full[stage], kHaloPatchBytes);
-          tma_load_4d(ring_a + stage * kHaloAStageBytes, &maps.m[src], c0, x0 - 1, y0 - 1, bb, &raw_full[stage]);
-        }
-        __syncwarp();
-        if (++stage == SA) stage = 0, phase ^= 1;
-        c0 += kBK;
-        if (c0 >= (src == 0 ? kl.src_c[0] : (src == 1 ? kl.src_c[1] : kl.src_c[2]))) c0 = 0, ++src;
-      }
-    }
-  } else {
-    // ============================================================ B loader
-    int stage = 0, phase = 0;
-    for (long long item = blockIdx.x; item < tw.total_items; item += gridDim.x) {
-      int bb, y0, x0, n_tile, u0, u1, part, tail_tile;
-      decode(item, bb, y0, x0, n_tile, u0, u1, part, tail_tile);
-      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) + (size_t)n_tile * wk.num_kb_total * Cfg::kBBytes;
-      for (int u = u0; u < u1; ++u) {
-        const int ch = u / 3, g = u - ch * 3;
-        mbar_wait(&b_empty[stage], phase ^ 1, 7);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&b_full[stage], Cfg::kBStageBytes);
-#pragma unroll
-          for (int t = 0; t < kTB; ++t)
-            bulk_g2s(ring_b + stage * Cfg::kBStageBytes + t * Cfg::kBBytes,
-                     wbase + (size_t)((g * kTB + t) * chunks + ch) * Cfg::kBBytes, Cfg::kBBytes, &b_full[stage]);
-        }
-        __syncwarp();
-        if (++stage == SB) stage = 0, phase ^= 1;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kMmaWarp) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-  }
-}
-
-// dst[tail tile] = act( sum_parts partial + bias (+ residual) ), parts added in order
-__global__ void halo_tail_reduce_kernel(const dtb200_conv_params p, TcWork wk, HaloTailWork tw, int bn,
-                                        const float* __restrict__ partial, int tail_tiles) {
-  const long long total = (long long)tail_tiles * kBM * (bn / 4);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % (bn / 4)) * 4;
-    const long long rr = i / (bn / 4);
-    const int row = (int)(rr % kBM), tail_tile = (int)(rr / kBM);
-    const long long tile = tw.full_items + tail_tile;
-    const int n_tile = (int)(tile % wk.n_tiles), m_tile = (int)(tile / wk.n_tiles);
-    const int per_img = wk.tiles_x * wk.tiles_y;
-    const int bb = m_tile / per_img, t = m_tile - bb * per_img;
-    const int oy = (t / wk.tiles_x) * kHaloTH + row / kHaloTW, ox = (t % wk.tiles_x) * kHaloTW + row % kHaloTW;
-    if (oy >= p.out_h || ox >= p.out_w) continue;
-    const float* src = partial + (((size_t)tail_tile * tw.parts) * kBM + row) * bn + c;
-    float4 a = ld4(src);
-    for (int part = 1; part < tw.parts; ++part) {
-      const float4 b = ld4(src + (size_t)part * kBM * bn);
-      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
-    }
-    const long long m = ((long long)bb * p.out_h + oy) * p.out_w + ox;
-    const long long o = m * p.out_c + n_tile * bn + c;
-    if (p.bias) {
-      const float4 b = ld4(p.bias + n_tile * bn + c);
-      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
-    }
-    if (p.residual) {
-      const float4 r = ld4(p.residual + o);
-      a.x += r.x, a.y += r.y, a.z += r.z, a.w += r.w;
-    }
-    a.x = activate(a.x, p.act, p.act_slope), a.y = activate(a.y, p.act, p.act_slope);
-    a.z = activate(a.z, p.act, p.act_slope), a.w = activate(a.w, p.act, p.act_slope);
-    *reinterpret_cast<float4*>(p.dst + o) = a;
-  }
-}
-
 // OIHW (out_c, in_c, k, k) -> per (N tile, K block): [B_big tile | B_small tile], each [BN rows][32 fp32] in the
 // SWIZZLE_128B K-major shared-memory image; K blocks follow KLayout (tap-major, per source 32-channel chunks, zero padded).
 __global__ void pack_weight_tc_kernel(const float* __restrict__ oihw, float* __restrict__ packed, int out_c, int in_c,
@@ -1112,7 +798,6 @@ int conv_tc_init() {
     cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true>::kSmemBytes);
     cudaFuncSetAttribute(conv_tc_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64, 1>::kSmemBytes);
     cudaFuncSetAttribute(conv_tc_halo_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64, 3>::kSmemBytes);
-    cudaFuncSetAttribute(conv_tc_halo_tail_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64, 3>::kSmemBytes);
     cudaGetLastError();
   });
   return g_num_sms_dev[dev];
@@ -1158,24 +843,6 @@ static bool halo_tiles(const dtb200_conv_params& p, int bn, int splits, TcWork* 
   return hw->total >= 148;
 }
 
-// Split of the last, partial persistent round along K (development switch, bit 4): see conv_tc_halo_tail_kernel.
-static bool halo_tail_plan(const TcWork& hw, int chunks, HaloTailWork* tw, int* tail_tiles) {
-  if (!(conv_flags() & 16) || (conv_flags() & 8)) return false;
-  const int rem = (int)(hw.total % 148);
-  if (rem == 0) return false;
-  const int units = 3 * chunks, max_parts = 148 / rem;
-  if (max_parts < 2 || units < 2) return false;
-  const int want = units < max_parts ? units : max_parts;
-  tw->upp = (units + want - 1) / want;
-  tw->parts = (units + tw->upp - 1) / tw->upp;
-  if (tw->parts < 2) return false;
-  tw->units = units;
-  tw->full_items = (int)(hw.total - rem);
-  tw->total_items = (long long)tw->full_items + (long long)rem * tw->parts;
-  *tail_tiles = rem;
-  return true;
-}
-
 uint64_t conv_tc_workspace_bytes(const dtb200_conv_params& p, int in_c_total) {
   if (p.ksize == 0 || p.out_c % 64 != 0) return 0;
   const long long m_total = (long long)p.batch * p.out_h * p.out_w;
@@ -1183,11 +850,6 @@ uint64_t conv_tc_workspace_bytes(const dtb200_conv_params& p, int in_c_total) {
   const KLayout kl = make_klayout(p.num_src, p.src_c, p.ksize);
   const int splits = tc_splits(tc_m_tiles(p), p.out_c, kl.num_kb);
   if (splits > 1) return (uint64_t)splits * m_total * p.out_c * sizeof(float);
-  TcWork hw;
-  HaloTailWork tw;
-  int tail_tiles = 0;
-  if (halo_tiles(p, tc_bn(p.out_c), splits, &hw) && halo_tail_plan(hw, kl.kb_per_tap, &tw, &tail_tiles))
-    return (uint64_t)tail_tiles * tw.parts * kBM * 64 * sizeof(float);
   return 0;
 }
 
@@ -1292,7 +954,7 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
 
   // 3x3 / stride-1 layers with at least one full round of 8 x 16 tiles: halo-tile kernel (one patch load + one split per
   // 9 taps).  Development switches: bit 7 of the flags turns it OFF (tap-major kernel everywhere), bit 3 selects the
-  // one-tap-per-weight-stage variant (default: 3 taps per stage), bit 4 splits the last partial round along K.
+  // one-tap-per-weight-stage variant (default: 3 taps per stage).
   {
     TcWork hw = wk;
     if (halo_tiles(p, bn, splits, &hw)) {
@@ -1311,19 +973,6 @@ int launch_conv_tc(const dtb200_conv_params& p, int in_c_total, cudaStream_t str
       }
       const int g_num_sms = conv_tc_init();
       const unsigned hgrid = (unsigned)(hw.total < g_num_sms ? hw.total : g_num_sms);
-      HaloTailWork tw;
-      int tail_tiles = 0;
-      if (halo_tail_plan(hw, kl.kb_per_tap, &tw, &tail_tiles) && p.workspace &&
-          p.workspace_bytes >= (uint64_t)tail_tiles * tw.parts * kBM * 64 * sizeof(float)) {
-        float* tail = reinterpret_cast<float*>(p.workspace);
-        const unsigned tgrid = (unsigned)(tw.total_items < g_num_sms ? tw.total_items : g_num_sms);
-        conv_tc_halo_tail_kernel<64><<<tgrid, kThreads, HaloCfg<64, 3>::kSmemBytes, stream>>>(p, hmaps, kl, hw, tw, tail);
-        int rc = check_launch("conv_tc_halo_tail_kernel");
-        if (rc != DTB200_OK) return rc;
-        const long long work = (long long)tail_tiles * kBM * (64 / 4);
-        halo_tail_reduce_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(p, hw, tw, 64, tail, tail_tiles);
-        return check_launch("halo_tail_reduce_kernel");
-      }
       if (conv_flags() & 8)  // one tap per weight-ring stage (6 stages): 51.2 us on the 240x320 64->64 layer vs 45.1 us
         conv_tc_halo_kernel<64, 1><<<hgrid, kThreads, HaloCfg<64, 1>::kSmemBytes, stream>>>(p, hmaps, kl, hw);
       else

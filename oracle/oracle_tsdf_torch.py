@@ -37,10 +37,23 @@ def frustum_bounds(invK_44, world_T_cam_44, min_depth, max_depth, img_h, img_w):
     return world.min(1).values[:3], world.max(1).values[:3]
 
 
+def frame_constants(cam_T_world_44, K_44, img_h, img_w, depth_max):
+    """The per-frame 4x4 work of integrate_depth (tools/tsdf.py:444-450 and the K @ T product of :405) on the device the
+    matrices live on: (P_34, box_lo_3, box_hi_3), all fp16."""
+    invK = torch.inverse(K_44[None].float()).half()[0]
+    world_T_cam = torch.inverse(cam_T_world_44[None].float()).half()[0]
+    lo, hi = frustum_bounds(invK, world_T_cam, 0.01, depth_max, img_h, img_w)
+    return torch.matmul(K_44[None], cam_T_world_44[None])[0, :3], lo, hi
+
+
 def integrate_depth(coords_3hwd, values, weights, voxel_size, depth_b1hw, cam_T_world_b44, K_b44, min_depth=0.5, max_depth=5.0,
-                    depth_mask_b1hw=None, extended_neg_truncation=False):
+                    depth_mask_b1hw=None, extended_neg_truncation=False, host_frame_constants=False):
     """In place on ``values`` / ``weights`` (fp16, same device as ``coords_3hwd``).  Every tensor op below is the
-    reference's, line for line in meaning; intermediate names follow tools/tsdf.py."""
+    reference's, line for line in meaning; intermediate names follow tools/tsdf.py.
+    ``host_frame_constants``: evaluate the per-frame 4x4 constants (two fp32 inverses, the frustum corners, K @ T) on the
+    CPU and move the fp16 results over -- a 4x4 fp16 product may round differently in cuBLAS than in ATen's CPU gemm, and one
+    flipped fp16 ulp in P moves every projected voxel; with the constants shared, a CUDA run isolates the per-voxel
+    arithmetic (projection, grid_sample, confidence, update) that the product's kernel restates."""
     dev = coords_3hwd.device
     truncation = TRUNCATION_SIZE * voxel_size
     dims = coords_3hwd.shape[1:]
@@ -57,14 +70,15 @@ def integrate_depth(coords_3hwd, values, weights, voxel_size, depth_b1hw, cam_T_
         K_144 = K_b44[b:b + 1].to(dev)
         depth_11hw = depth_b1hw[b:b + 1]
         depth_max = max_depth + truncation + 0.1
-        invK = torch.inverse(K_144.float()).half()
-        world_T_cam = torch.inverse(T_144.float()).half()
-        lo, hi = frustum_bounds(invK[0], world_T_cam[0], 0.01, depth_max, img_h, img_w)
+        if host_frame_constants:
+            P_34, lo, hi = (t.to(dev) for t in frame_constants(cam_T_world_b44[b].cpu(), K_b44[b].cpu(), img_h, img_w, depth_max))
+        else:
+            P_34, lo, hi = frame_constants(T_144[0], K_144[0], img_h, img_w, depth_max)
         c = hom_14N[0, :3]
         in_box = torch.logical_and(c > lo.view(3, 1), c < hi.view(3, 1)).all(0)
         idx = in_box.nonzero().squeeze(1)
         vox_14N = hom_14N[..., in_box]
-        P_134 = torch.matmul(K_144, T_144)[:, :3]
+        P_134 = P_34[None]
         cam_13N = torch.matmul(P_134, vox_14N)
         cam_13N[:, :2] = cam_13N[:, :2] / cam_13N[:, 2, None]
         vz = cam_13N[:, 2:3]

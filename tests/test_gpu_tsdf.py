@@ -100,9 +100,11 @@ def test_aten_cuda_semantics_match_torch_cuda_ops(name):
     """pin the DEFAULT (aten_cuda) branch against ATen's own CUDA kernels.  oracle_tsdf_torch.integrate_depth is
     the reference's op sequence (bit-exact against the fixtures on the CPU, tests/test_oracle_tsdf_golden.py); here it
     runs on the GPU, where torch's CUDA grid_sample / fp16 elementwise kernels / cuBLAS decide every rounding.
-    cuBLAS evaluates the (3x4)@(4xN) fp16 projection with its own accumulation order, which may flip an fp16 rounding on
-    a handful of voxels (and then, through the nearest-pixel lookup, their sampled depth): the bar is >= 99.9 % of the
-    touched voxels bit-identical, the count is printed."""
+    The per-frame 4x4 constants (P = K @ T, frustum box) are evaluated on the host on both sides (host_frame_constants: a
+    4x4 fp16 product may round differently in cuBLAS, and one flipped ulp in P moves every voxel -- measured: 2 % of the
+    voxels differ then).  cuBLAS still evaluates the (3x4)@(4xN) projection with its own accumulation order, which may flip
+    an fp16 rounding on a handful of voxels (and then, through the nearest-pixel lookup, their sampled depth): the bar is
+    >= 99.9 % of the touched voxels bit-identical, the counts are printed."""
     from oracle import oracle_tsdf_torch as ott
 
     fx = hp.load(name)
@@ -116,7 +118,7 @@ def test_aten_cuda_semantics_match_torch_cuda_ops(name):
                             torch.from_numpy(fx["cam_T_world"][s:s + fb]).cuda(), torch.from_numpy(fx["K"][s:s + fb]).cuda(),
                             min_depth=0.5, max_depth=float(fx["max_depth"]),
                             depth_mask_b1hw=torch.from_numpy(fx["mask"][s:s + fb]).cuda() if with_mask else None,
-                            extended_neg_truncation=bool(ext))
+                            extended_neg_truncation=bool(ext), host_frame_constants=True)
     torch.cuda.synchronize()
     touched = int((weights > 0).sum())
     dv = int((bits(vol.tsdf_values) != bits(values)).sum())
