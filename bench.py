@@ -199,7 +199,8 @@ def run_b200(args):
     cfg = syn.CONFIGS[WORKLOAD]
     opts = dt.HotPathOptions(matching_num_depth_bins=cfg.planes, model_num_views=cfg.num_src + 1,
                              image_height=cfg.image_h, image_width=cfg.image_w)
-    model = dt.DepthModelCVHint(opts, math=args.math, volume_math=args.volume_math or args.math)
+    volume_math = args.volume_math or ("exact" if args.math == "exact" else "tch")
+    model = dt.DepthModelCVHint(opts, math=args.math, volume_math=volume_math)
     model.load_state_dict(model_weights(model), strict=False)
     model = model.to(dev)
 
@@ -304,7 +305,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.math == "exact" else "f32 via 3xTF32 (tf32 big/small split, fp32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC, "math": args.math, "frames_per_step": frames_per_step,
+            "config": {"workload": WORKLOAD_DESC, "math": args.math, "volume_math": volume_math, "frames_per_step": frames_per_step,
                        "l2": "256 MiB L2 flush between timed steps (outside the per-step event pairs); 4 rotating input sets",
                        "weights": "random-init (seeded), reference architecture",
                        "wall_ms_per_step_incl_flush": round(1e3 * t_wall / args.steps, 4)},
@@ -504,7 +505,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--math", default="tc3x", choices=["exact", "tc3x"],
                     help="tc3x: tcgen05 tensor cores with the 3xTF32 split (fp32-class, parity-green); exact: fp32 CUDA cores")
-    ap.add_argument("--volume-math", default=None, choices=["exact", "tc3x"])
+    ap.add_argument("--volume-math", default=None, choices=["exact", "tc3x", "tch"],
+                    help="cost-volume MLP arithmetic; default: tch (kind::f16, 2-term fp16 split) unless --math exact")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--ref-budget", type=float, default=150.0)

@@ -13,11 +13,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdoubletake_b200.so")
 
 VOLUME_DOT, VOLUME_MLP, VOLUME_MLP_HINT = 0, 1, 2
-MATH_EXACT, MATH_TC3X = 0, 1
+MATH_EXACT, MATH_TC3X, MATH_TCH = 0, 1, 2
 RESAMPLE_NONE, RESAMPLE_BILINEAR_UP2, RESAMPLE_NEAREST_UP2 = 0, 1, 2
 ACT_NONE, ACT_LEAKY, ACT_ELU = 0, 1, 2
 CONV_MAX_SRC = 3
-MATH_NAMES = {"exact": MATH_EXACT, "tc3x": MATH_TC3X}
+MATH_NAMES = {"exact": MATH_EXACT, "tc3x": MATH_TC3X, "tch": MATH_TCH}
 
 fp = C.c_void_p
 
@@ -53,7 +53,7 @@ class ConvParams(C.Structure):
 
 
 TSDF_MAX_FRAMES = 8
-TSDF_SEMANTICS = {"aten_cpu": 0, "aten_cuda": 1}
+TSDF_SEMANTICS = {"aten_cpu": 0, "aten_cuda": 1, "aten_cuda_half_index": 2}
 
 
 class TsdfFrame(C.Structure):

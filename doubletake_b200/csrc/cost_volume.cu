@@ -392,21 +392,27 @@ static size_t mlp_exact_smem(int K) {
 int launch_cost_volume_tc(const dtb200_cost_volume_params& p, cudaStream_t stream);       // cost_volume_tc.cu
 int prepare_cost_volume_tc(const dtb200_cost_volume_params& p, cudaStream_t stream);      // cost_volume_tc.cu
 uint64_t cost_volume_tc_workspace_bytes(const dtb200_cost_volume_params& p);              // cost_volume_tc.cu
+int launch_cost_volume_tch(const dtb200_cost_volume_params& p, cudaStream_t stream);      // cost_volume_tch.cu
+int prepare_cost_volume_tch(const dtb200_cost_volume_params& p, cudaStream_t stream);     // cost_volume_tch.cu
+uint64_t cost_volume_tch_workspace_bytes(const dtb200_cost_volume_params& p);             // cost_volume_tch.cu
 
 }  // namespace dtb200
 
 using namespace dtb200;
 
 extern "C" uint64_t dtb200_cost_volume_workspace_bytes(const dtb200_cost_volume_params* p) {
-  if (!p || p->math != DTB200_MATH_TC3X || p->kind == DTB200_VOLUME_DOT || p->views < 1 || p->views > DTB200_MAX_VIEWS) return 0;
+  if (!p || p->kind == DTB200_VOLUME_DOT || p->views < 1 || p->views > DTB200_MAX_VIEWS) return 0;
+  if (p->math == DTB200_MATH_TCH) return (p->batch < 1 || p->height < 1 || p->width < 1) ? 0 : cost_volume_tch_workspace_bytes(*p);
+  if (p->math != DTB200_MATH_TC3X) return 0;
   return cost_volume_tc_workspace_bytes(*p);
 }
 
 extern "C" int dtb200_cost_volume_prepare(const dtb200_cost_volume_params* p, dtb200_stream_t stream) {
   if (!p) return fail(DTB200_ERR_INVALID, "cost_volume_prepare: null params%s");
-  if (p->math != DTB200_MATH_TC3X || p->kind == DTB200_VOLUME_DOT) return DTB200_OK;
-  if (!p->w1 || !p->w2 || p->views < 1 || p->views > DTB200_MAX_VIEWS)
+  if ((p->math != DTB200_MATH_TC3X && p->math != DTB200_MATH_TCH) || p->kind == DTB200_VOLUME_DOT) return DTB200_OK;
+  if (!p->w1 || !p->w2 || !p->b1 || p->views < 1 || p->views > DTB200_MAX_VIEWS)
     return fail(DTB200_ERR_INVALID, "cost_volume_prepare: weights / views missing%s");
+  if (p->math == DTB200_MATH_TCH) return prepare_cost_volume_tch(*p, (cudaStream_t)stream);
   return prepare_cost_volume_tc(*p, (cudaStream_t)stream);
 }
 
@@ -447,6 +453,7 @@ extern "C" int dtb200_cost_volume(const dtb200_cost_volume_params* pp, dtb200_st
                !p.hb3 || p.hint_height < 1 || p.hint_width < 1))
     return fail(DTB200_ERR_INVALID, "cost volume: hint inputs / hint MLP weights missing%s");
   if (p.math == DTB200_MATH_TC3X) return launch_cost_volume_tc(p, stream);
+  if (p.math == DTB200_MATH_TCH) return launch_cost_volume_tch(p, stream);
   if (p.math != DTB200_MATH_EXACT) return fail(DTB200_ERR_INVALID, "cost volume: unknown math mode %s%lld", "", p.math);
   size_t smem = mlp_exact_smem(p.views);
   dim3 grid(ceil_div(HW, kPixPerWarp), p.batch);

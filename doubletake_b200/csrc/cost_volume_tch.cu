@@ -1,0 +1,729 @@
+// Fused plane-sweep feature volume, second generation: persistent, warp-specialised, tcgen05 kind::f16 with the 2-term
+// fp16 operand split (math = TCH), sm_100a.
+//
+// FeatureVolumeManager / FeatureMeshHintVolumeManager (reference modules/feature_volume.py:186-352,
+// modules/mesh_hint_volume.py:209-393).  One CTA per SM walks a contiguous range of work items; an item is 16 pixels x 8
+// depth planes = 128 rows of the per-plane MLP (the reference evaluates the MLP once per plane over all pixels).
+//
+//   producers (8 or 16 warps)   backproject / project / bilinear warp of the K source maps (the same fp32 geometry code
+//                               as the exact kernel), dot products, ray metadata -> GEMM1 operand tiles, written
+//                               straight into SWIZZLE_128B K-major shared memory as fp16 (big | small); the 26K+20
+//                               channel tensor of the reference never exists
+//   MMA warp                    GEMM1: D1[128 x 128] += rows x W1'^T, GEMM2: D2 += h1 x W2'^T; three kind::f16 MMAs per
+//                               16-wide K step (small*big + big*small + big*big), fp32 accumulators in TMEM, both
+//                               double-buffered (4 x 128 columns), GEMM2 of item i issued AFTER GEMM1 of item i+1 so the
+//                               epilogue that sits between them never stalls the tensor pipe
+//   weight loader warp          cp.async.bulk of the pre-packed weight tile of every K block (L2 -> shared memory ring)
+//   epilogue (8 warps)          epilogue-1: D1 -> LeakyReLU -> fp16 split -> GEMM2 operand tiles (never leaves the SM);
+//                               epilogue-2: D2 -> +b2, LeakyReLU, . w3 + b3 -> hint MLP (3-12-12-1, fp32) -> volume
+//                               store; arg-max over planes through one packed-key atomicMax per pixel and item
+//
+// K layout of GEMM1 (ours to choose: W1 is re-packed once): one 32-channel SLOT per source view -- 16 warped feature
+// channels, then mask, source depth, dot product, ray angle, source ray (3), combined pose distance, R measure,
+// t measure, 6 zeros -- and one slot for the current view: 16 features, plane depth, current ray (3), a constant 1
+// whose weight column holds the bias b1, zeros.  Everything a (pixel, plane, view) produces lands in ONE K block, so the
+// producers need no metadata staging buffer and no barrier among themselves.  Two slots = one 64-channel K block.
+//
+// Precision: x = big + small with big = fp16(x), small = fp16(x - big) (inputs of this MLP are O(1) by construction:
+// instance-normalised features, unit rays, depths of a few metres -- absolute error <= max(2^-22 |x|, 2^-25));
+// weights are pre-scaled by a power of two per layer so that big + small carries 22 bits of every weight, the scale is
+// undone exactly in the epilogues.  Per-product error ~2^-21, the same class as the 3xTF32 kernel it replaces, at half
+// the operand bytes and twice the tensor-core rate.
+#include <mutex>
+
+#include "common.cuh"
+#include "cv_common.cuh"
+#include "tc_common.cuh"
+
+namespace dtb200 {
+
+using namespace tc;
+
+constexpr int kHRows = 128;                 // rows per item = 8 planes x 16 pixels
+constexpr int kHPix = 16;
+constexpr int kHPlanes = 8;
+constexpr int kHHidden = 128;
+constexpr int kHEpiWarps = 8;               // warps 0-7: TMEM lane quadrant = warp & 3, column half = warp >> 2
+constexpr int kHTile = kHRows * 128;        // 16 KB: [128 rows][64 fp16], one of big / small
+constexpr int kHAStage = 2 * kHTile;        // A_big | A_small
+constexpr int kHBStage = 2 * kHTile;        // W_big | W_small
+constexpr int kHAStages = 4;
+constexpr int kHBStages = 2;
+constexpr int kHSlot = 32;                  // channels per slot
+constexpr int kHHeaderBytes = 256;          // workspace header: scale1, 1/scale1, scale2, 1/scale2
+
+__host__ __device__ inline int cvh_nkb1(int K) { return (K + 2) / 2; }   // ceil((K + 1) slots / 2)
+
+// shared-memory carve-up after the two rings
+struct CvhSmall {
+  ViewConst vc[DTB200_MAX_VIEWS];
+  float b2[kHHidden], w3[kHHidden];
+  float hw[224];                 // hint MLP: hw1 (36) hb1 (12) hw2 (144) hb2 (12) hw3 (12) hb3 (1)
+  float partial[2][kHRows];
+  float score[kHRows];
+  uint64_t a_full[kHAStages], a_empty[kHAStages], b_full[kHBStages], b_empty[kHBStages];
+  uint64_t d1_full[2], d2_full[2], d2_empty[2];
+  uint32_t tmem_slot;
+};
+constexpr size_t kHSmemBytes = 1024 + (size_t)kHAStages * kHAStage + (size_t)kHBStages * kHBStage + sizeof(CvhSmall);
+
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// x -> (fp16(x), fp16(x - fp16(x))) for a pair; no clamp (callers clamp the few unbounded channels)
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& big, uint32_t& small) {
+  const __half2 b = __floats2half2_rn(x0, x1);
+  const float2 bf = __half22float2(b);
+  const __half2 s = __floats2half2_rn(x0 - bf.x, x1 - bf.y);
+  big = *reinterpret_cast<const uint32_t*>(&b);
+  small = *reinterpret_cast<const uint32_t*>(&s);
+}
+__device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -kHalfMax), kHalfMax); }
+
+// order-preserving key of (score, plane): larger score wins, then the smaller plane index (torch.argmax: first maximum;
+// NaN is maximal).  -0 is canonicalised to +0 so that equal values tie on the index.
+__device__ __forceinline__ unsigned long long argmax_key(float v, int plane) {
+  uint32_t u;
+  if (isnan(v)) {
+    u = 0xFFFFFFFFu;
+  } else {
+    u = __float_as_uint(v + 0.f);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  }
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)plane);
+}
+
+struct CvhWork {
+  int pix_groups, plane_chunks;   // per batch element
+  int total;                      // batch * pix_groups * plane_chunks (checked to fit 31 bits by the launcher)
+};
+
+template <bool kHint, int kProdWarps>
+__global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
+    cv_mlp_tch_kernel(const dtb200_cost_volume_params p, const uint8_t* __restrict__ wpack, unsigned long long* __restrict__ keys,
+                      CvhWork wk) {
+  constexpr int kMmaWarp = kHEpiWarps + kProdWarps;
+  constexpr int kLoadWarp = kMmaWarp + 1;
+  constexpr int kProdThreads = kProdWarps * 32;
+  constexpr int kRowsPerThread = kHRows * 4 / kProdThreads;   // 1 (16 warps) or 2 (8 warps)
+  constexpr int S = kHAStages, SB = kHBStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring_a = smem;
+  uint8_t* ring_b = ring_a + S * kHAStage;
+  CvhSmall& sm = *reinterpret_cast<CvhSmall*>(ring_b + SB * kHBStage);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.views;
+  const int nkb1 = cvh_nkb1(K);
+  const int HW = p.height * p.width;
+  const float* hdr = reinterpret_cast<const float*>(wpack);
+  const uint8_t* w1p = wpack + kHHeaderBytes;
+  const uint8_t* w2p = w1p + (size_t)nkb1 * kHBStage;
+
+  // contiguous item range of this CTA
+  const int it_begin = (int)((long long)wk.total * blockIdx.x / gridDim.x);
+  const int it_end = (int)((long long)wk.total * (blockIdx.x + 1) / gridDim.x);
+  const int n = it_end - it_begin;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&sm.a_full[s], kProdWarps), mbar_init(&sm.a_empty[s], 1);
+    for (int s = 0; s < SB; ++s) mbar_init(&sm.b_full[s], 1), mbar_init(&sm.b_empty[s], 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&sm.d1_full[s], 1), mbar_init(&sm.d2_full[s], 1), mbar_init(&sm.d2_empty[s], kHEpiWarps);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < kHHidden; i += blockDim.x) sm.b2[i] = p.b2[i], sm.w3[i] = p.w3[i];
+  if (kHint) {
+    for (int i = tid; i < 217; i += blockDim.x) {
+      float v;
+      if (i < 36) v = p.hw1[i];
+      else if (i < 48) v = p.hb1[i - 36];
+      else if (i < 192) v = p.hw2[i - 48];
+      else if (i < 204) v = p.hb2[i - 192];
+      else if (i < 216) v = p.hw3[i - 204];
+      else v = p.hb3[0];
+      sm.hw[i] = v;
+    }
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(&sm.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_slot;
+
+  // global K-block sequence numbers (the order the MMA warp consumes A / B stages in):
+  //   G1(0) | G1(1) G2(0) | G1(2) G2(1) | ... | G1(n-1) G2(n-2) | G2(n-1)
+  // (32-bit unsigned: a CTA sees at most total / gridDim items, each worth nkb1 + 2 <= 11 K blocks)
+  auto g1 = [&](int it, int kb) -> uint32_t { return it == 0 ? (uint32_t)kb : (uint32_t)(nkb1 + (it - 1) * (nkb1 + 2) + kb); };
+  auto g2 = [&](int it, int j) -> uint32_t {
+    return it < n - 1 ? (uint32_t)(nkb1 + it * (nkb1 + 2) + nkb1 + j) : (uint32_t)(nkb1 + (n - 1) * (nkb1 + 2) + j);
+  };
+  auto decode = [&](int it, int& b, int& pix0, int& d0) {
+    const uint32_t item = (uint32_t)(it_begin + it);
+    const uint32_t per_b = (uint32_t)(wk.pix_groups * wk.plane_chunks);
+    const uint32_t bb = item / per_b, r = item - bb * per_b;
+    const uint32_t pg = r / (uint32_t)wk.plane_chunks;
+    b = (int)bb;
+    pix0 = (int)pg * kHPix;
+    d0 = (int)(r - pg * (uint32_t)wk.plane_chunks) * kHPlanes;
+  };
+
+  if (n <= 0) {
+    // nothing to do (more CTAs than items)
+  } else if (warp < kHEpiWarps) {
+    // ==================================================================================================== epilogue
+    const int qd = warp & 3, half = warp >> 2;
+    const int row = qd * 32 + lane;          // TMEM lane == row of the item
+    const int rpi = row & 15, rdp = row >> 4;
+    const float inv1 = hdr[1], inv2 = hdr[3];
+    const float b3 = __ldg(p.b3);
+    const uint32_t lane_bits = (uint32_t)(qd * 32) << 16;
+    const uint32_t ring_u = smem_u32(ring_a);
+
+    auto epi1 = [&](int it) {
+      const int buf = it & 1;
+      mbar_wait(&sm.d1_full[buf], (it >> 1) & 1, 20);
+      tc_fence_after();
+      const uint32_t g = g2(it, half);
+      const int st = (int)(g % S);
+      mbar_wait(&sm.a_empty[st], (uint32_t)(((g / S) & 1) ^ 1), 21);
+      const uint32_t a_big = ring_u + (uint32_t)st * kHAStage;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        float v[32];
+        tmem_ld32(tmem_base + (uint32_t)(buf * kHHidden) + lane_bits + (uint32_t)(64 * half + 32 * cc), v);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t bg[4], sl[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            split_pair(leaky01_fast(v[8 * ch + 2 * j] * inv1), leaky01_fast(v[8 * ch + 2 * j + 1] * inv1), bg[j], sl[j]);
+          const uint32_t off = (uint32_t)row * 128u + (uint32_t)(((4 * cc + ch) ^ (row & 7)) << 4);
+          sts128u(a_big + off, bg[0], bg[1], bg[2], bg[3]);
+          sts128u(a_big + kHTile + off, sl[0], sl[1], sl[2], sl[3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_n(&sm.a_full[st], kProdWarps / 4);  // 4 warps fill one h1 block
+    };
+
+    auto epi2 = [&](int it) {
+      const int buf = it & 1;
+      mbar_wait(&sm.d2_full[buf], (it >> 1) & 1, 22);
+      tc_fence_after();
+      float s = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        float v[32];
+        const int n0 = 64 * half + 32 * cc;
+        tmem_ld32(tmem_base + (uint32_t)(2 * kHHidden + buf * kHHidden) + lane_bits + (uint32_t)n0, v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {  // b2 / w3 as 16-byte broadcast loads
+          const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[n0 + j]);
+          const float4 ww = *reinterpret_cast<const float4*>(&sm.w3[n0 + j]);
+          s = fmaf(leaky01_fast(fmaf(v[j], inv2, bb.x)), ww.x, s);
+          s = fmaf(leaky01_fast(fmaf(v[j + 1], inv2, bb.y)), ww.y, s);
+          s = fmaf(leaky01_fast(fmaf(v[j + 2], inv2, bb.z)), ww.z, s);
+          s = fmaf(leaky01_fast(fmaf(v[j + 3], inv2, bb.w)), ww.w, s);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.d2_empty[buf]);  // D2[buf] drained
+      sm.partial[half][row] = s;
+      named_bar(2, kHEpiWarps * 32);
+      if (half == 0) {
+        int b, pix0, d0;
+        decode(it, b, pix0, d0);
+        const int d = d0 + rdp, opix = pix0 + rpi;
+        float score = sm.partial[0][row] + sm.partial[1][row] + b3;
+        if (kHint) {
+          const int ppix = min(opix, HW - 1);
+          const int py = ppix / p.width, px = ppix - py * p.width;
+          const int sy = min((int)floorf((float)py * ((float)p.hint_height / (float)p.height)), p.hint_height - 1);
+          const int sx = min((int)floorf((float)px * ((float)p.hint_width / (float)p.width)), p.hint_width - 1);
+          const long long o = ((long long)b * p.hint_height + sy) * p.hint_width + sx;
+          const bool valid = __ldg(p.hint_mask + o) != 0.f;
+          const float dd = plane_depth(p, b, min(d, p.planes - 1), ppix);
+          const float in[3] = {score, valid ? fabsf(DT_SUB(__ldg(p.depth_hint + o), dd)) : -1.f, valid ? __ldg(p.hint_weights + o) : 0.f};
+          const float* hw1 = sm.hw, *hb1 = sm.hw + 36, *hw2 = sm.hw + 48, *hb2 = sm.hw + 192, *hw3 = sm.hw + 204;
+          float h1[12], h2[12];
+#pragma unroll
+          for (int o2 = 0; o2 < 12; ++o2) {
+            float a = hb1[o2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) a = DT_FMA(in[i], hw1[o2 * 3 + i], a);
+            h1[o2] = leaky01_fast(a);
+          }
+#pragma unroll
+          for (int o2 = 0; o2 < 12; ++o2) {
+            float a = hb2[o2];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) a = DT_FMA(h1[i], hw2[o2 * 12 + i], a);
+            h2[o2] = leaky01_fast(a);
+          }
+          float a = sm.hw[216];
+#pragma unroll
+          for (int i = 0; i < 12; ++i) a = DT_FMA(h2[i], hw3[i], a);
+          score = a;
+        }
+        if (d < p.planes && opix < HW) p.volume[((long long)b * p.planes + d) * HW + opix] = score;
+        sm.score[row] = score;
+      }
+      named_bar(2, kHEpiWarps * 32);
+      if (warp == 0 && lane < kHPix) {
+        int b, pix0, d0;
+        decode(it, b, pix0, d0);
+        const int opix = pix0 + lane;
+        if (opix < HW) {
+          unsigned long long best = 0ull;
+          for (int w = 0; w < kHPlanes && d0 + w < p.planes; ++w) {
+            const unsigned long long k = argmax_key(sm.score[w * kHPix + lane], d0 + w);
+            best = k > best ? k : best;
+          }
+          atomicMax(keys + (long long)b * HW + opix, best);
+        }
+      }
+    };
+
+    for (int it = 0; it < n; ++it) {
+      epi1(it);
+      if (it > 0) epi2(it - 1);
+    }
+    epi2(n - 1);
+  } else if (warp < kMmaWarp) {
+    // ==================================================================================================== producers
+    const int pt = tid - kHEpiWarps * 32;
+    const int q = pt & 3;
+    const int rbase = pt >> 2;   // row of this thread (rows rbase and rbase + 64 with 8 producer warps)
+    const float invW = 1.f / (float)p.width, invH = 1.f / (float)p.height;
+    const int npass = (K + 4) / 4;   // ceil((K + 1) slots / 4)
+    const uint32_t ring_u = smem_u32(ring_a);
+    int cur_b = -1;
+
+    for (int it = 0; it < n; ++it) {
+      int b, pix0, d0;
+      decode(it, b, pix0, d0);
+      if (b != cur_b) {  // (re)load the per-view constants of this batch element
+        named_bar(1, kProdThreads);
+        if (pt < K)
+          load_view_const(sm.vc[pt], p.src_Ks + ((long long)b * K + pt) * 16, p.src_extrinsics + ((long long)b * K + pt) * 16,
+                          p.src_poses + ((long long)b * K + pt) * 16);
+        named_bar(1, kProdThreads);
+        cur_b = b;
+      }
+      // ---- per-row state
+      float X[kRowsPerThread][3], an[kRowsPerThread][3], rc[kRowsPerThread][3], depth[kRowsPerThread];
+      float4 cur[kRowsPerThread];
+      int pixs[kRowsPerThread];
+      bool live[kRowsPerThread], lastp[kRowsPerThread], any_d[kRowsPerThread], any_b[kRowsPerThread];
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerThread; ++rr) {
+        const int row = rbase + 64 * rr;
+        const int pix = pix0 + (row & 15);
+        live[rr] = pix < HW;
+        const int pixc = live[rr] ? pix : HW - 1;
+        pixs[rr] = pix;
+        const int y = pixc / p.width, x = pixc - y * p.width;
+        float r[3];
+        backproject_ray(p.cur_invK + b * 16, x, y, r);
+        const float* c = p.cur_feats + ((long long)b * kC + q * 4) * HW + pixc;
+        cur[rr] = make_float4(__ldg(c), __ldg(c + HW), __ldg(c + 2 * HW), __ldg(c + 3 * HW));
+        const int dreal = d0 + (row >> 4);
+        const int d = min(dreal, p.planes - 1);
+        lastp[rr] = (dreal == p.planes - 1);
+        depth[rr] = plane_depth(p, b, d, pixc);
+        X[rr][0] = DT_MUL(depth[rr], r[0]), X[rr][1] = DT_MUL(depth[rr], r[1]), X[rr][2] = DT_MUL(depth[rr], r[2]);
+        float nn = DT_MUL(X[rr][0], X[rr][0]);
+        nn = DT_FMA(X[rr][1], X[rr][1], nn);
+        nn = DT_FMA(X[rr][2], X[rr][2], nn);
+        // F.normalize (eps 1e-12) and the cosine-similarity normalisation (eps 1e-5) through reciprocal square roots: these
+        // values feed a split-fp16 GEMM, ~1 ulp differences against the exact kernel's IEEE divisions are irrelevant here
+        const float inc = rsqrtf(fmaxf(nn, 1e-24f));
+        rc[rr][0] = X[rr][0] * inc, rc[rr][1] = X[rr][1] * inc, rc[rr][2] = X[rr][2] * inc;
+        const float in1 = rsqrtf(fmaxf(rc[rr][0] * rc[rr][0] + rc[rr][1] * rc[rr][1] + rc[rr][2] * rc[rr][2], 1e-10f));
+        an[rr][0] = rc[rr][0] * in1, an[rr][1] = rc[rr][1] * in1, an[rr][2] = rc[rr][2] * in1;
+        any_d[rr] = any_b[rr] = false;
+      }
+
+      for (int pass = 0; pass < npass; ++pass) {
+        const int kb0 = 2 * pass;
+        const bool has_b = kb0 + 1 < nkb1;
+        const uint32_t gA = g1(it, kb0), gB = gA + 1;
+        const int stA = (int)(gA % S), stB = (int)(gB % S);
+        mbar_wait(&sm.a_empty[stA], (uint32_t)(((gA / S) & 1) ^ 1), 10);
+        if (has_b) mbar_wait(&sm.a_empty[stB], (uint32_t)(((gB / S) & 1) ^ 1), 11);
+        const uint32_t baseA = ring_u + (uint32_t)stA * kHAStage, baseB = ring_u + (uint32_t)stB * kHAStage;
+        const int my_slot = 4 * pass + q;   // the slot whose per-(row, view) scalar work this lane does
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerThread; ++rr) {
+          const int row = rbase + 64 * rr;
+          const uint32_t row_off = (uint32_t)row * 128u;
+          const int rx = row & 7;
+          // ---- (a) scalar work of my slot: projection, sampling setup, masks, source ray, ray angle
+          SampleSetup mine;
+          mine.off = 0, mine.mask = 0, mine.w[0] = mine.w[1] = mine.w[2] = mine.w[3] = 0.f;
+          float my_m = 0.f;
+          float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f, m5 = 0.f, m6 = 0.f, m7 = 0.f, m8 = 0.f, m9 = 0.f;
+          if (my_slot < K) {
+            const ViewConst& vc = sm.vc[my_slot];
+            const Projected pr = project_point(vc, X[rr][0], X[rr][1], X[rr][2]);
+            mine = sample_setup(pr.u, pr.v, p.height, p.width, invW, invH);
+            const bool depth_ok = pr.zp > 0.f;
+            my_m = depth_ok ? 1.f : 0.f;
+            if (lastp[rr] && live[rr]) {
+              const bool bounds = (pr.u > 2.f) && (pr.u < (float)(p.width - 2)) && (pr.v > 2.f) && (pr.v < (float)(p.height - 2));
+              write_masks(p, b, pixs[rr], my_slot, depth_ok, bounds, any_d[rr], any_b[rr]);
+            }
+            // source ray normalize(X - t_src) and cos(cur ray, src ray) (reciprocal square roots: the operands feed a
+            // split-fp16 GEMM, ~1 ulp differences are irrelevant here)
+            const float y0 = X[rr][0] - vc.t[0], y1 = X[rr][1] - vc.t[1], y2 = X[rr][2] - vc.t[2];
+            const float inv = rsqrtf(fmaxf(y0 * y0 + y1 * y1 + y2 * y2, 1e-24f));
+            const float rs0 = y0 * inv, rs1 = y1 * inv, rs2 = y2 * inv;
+            const float inv2 = rsqrtf(fmaxf(rs0 * rs0 + rs1 * rs1 + rs2 * rs2, 1e-10f));
+            m0 = my_m, m1 = clamp_h(pr.zp);
+            m3 = (an[rr][0] * rs0 + an[rr][1] * rs1 + an[rr][2] * rs2) * inv2;
+            m4 = rs0, m5 = rs1, m6 = rs2, m7 = vc.comb, m8 = vc.rm, m9 = vc.tm;
+          } else if (my_slot == K) {
+            m0 = depth[rr], m1 = rc[rr][0], m2 = rc[rr][1], m3 = rc[rr][2], m4 = 1.f;   // 1 x (bias column of W1')
+          }
+          // ---- (b) every lane gathers its 4 channels of each of the pass's 4 slots and stores them
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int slot = 4 * pass + c;
+            if (slot > K) break;
+            float4 feat;
+            if (slot < K) {
+              const int srcl = (lane & ~3) | c;
+              SampleSetup ss;
+              ss.off = __shfl_sync(0xffffffffu, mine.off, srcl);
+              ss.mask = __shfl_sync(0xffffffffu, mine.mask, srcl);
+              ss.w[0] = __shfl_sync(0xffffffffu, mine.w[0], srcl);
+              ss.w[1] = __shfl_sync(0xffffffffu, mine.w[1], srcl);
+              ss.w[2] = __shfl_sync(0xffffffffu, mine.w[2], srcl);
+              ss.w[3] = __shfl_sync(0xffffffffu, mine.w[3], srcl);
+              const float m = __shfl_sync(0xffffffffu, my_m, srcl);
+              const float* sv = p.src_feats_nhwc + ((long long)b * K + slot) * HW * kC;
+              feat = sample_apply_nb(sv, q, ss, p.width);
+              const float dot = DT_MUL(quad_dot(feat, cur[rr]), m);
+              if (q == c) m2 = clamp_h(dot);
+            } else {
+              feat = cur[rr];
+            }
+            uint32_t b0, s0, b1, s1;
+            split_pair(feat.x, feat.y, b0, s0);
+            split_pair(feat.z, feat.w, b1, s1);
+            const uint32_t base = (c < 2) ? baseA : baseB;
+            const uint32_t off = row_off + (uint32_t)(((4 * (c & 1) + (q >> 1)) ^ rx) << 4) + (uint32_t)((q & 1) << 3);
+            sts64(base + off, b0, b1);
+            sts64(base + kHTile + off, s0, s1);
+          }
+          // ---- (c) the owner lane stores its slot's 16 metadata channels (two 16-byte chunks)
+          if (my_slot <= K) {
+            uint32_t bg[4], sl[4];
+            split_pair(m0, m1, bg[0], sl[0]);
+            split_pair(m2, m3, bg[1], sl[1]);
+            split_pair(m4, m5, bg[2], sl[2]);
+            split_pair(m6, m7, bg[3], sl[3]);
+            const uint32_t base = (q < 2) ? baseA : baseB;
+            const uint32_t off2 = row_off + (uint32_t)(((4 * (q & 1) + 2) ^ rx) << 4);
+            const uint32_t off3 = row_off + (uint32_t)(((4 * (q & 1) + 3) ^ rx) << 4);
+            sts128u(base + off2, bg[0], bg[1], bg[2], bg[3]);
+            sts128u(base + kHTile + off2, sl[0], sl[1], sl[2], sl[3]);
+            split_pair(m8, m9, bg[0], sl[0]);
+            sts128u(base + off3, bg[0], 0u, 0u, 0u);
+            sts128u(base + kHTile + off3, sl[0], 0u, 0u, 0u);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&sm.a_full[stA]);
+          if (has_b) mbar_arrive(&sm.a_full[stB]);
+        }
+      }
+      // ---- any-view mask of the last plane: the 4 lanes of a quad own different slots of every pass
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerThread; ++rr) {
+        int dflag = any_d[rr], bflag = any_b[rr];
+        dflag |= __shfl_xor_sync(0xffffffffu, dflag, 1);
+        bflag |= __shfl_xor_sync(0xffffffffu, bflag, 1);
+        dflag |= __shfl_xor_sync(0xffffffffu, dflag, 2);
+        bflag |= __shfl_xor_sync(0xffffffffu, bflag, 2);
+        if (q == 0 && p.mask_any && lastp[rr] && live[rr]) p.mask_any[(long long)b * HW + pixs[rr]] = (dflag && bflag) ? 1 : 0;
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ==================================================================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_f16(kHRows, kHHidden);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t ring_a_u = smem_u32(ring_a), ring_b_u = smem_u32(ring_b);
+    auto block = [&](uint32_t g, int ksteps, uint32_t tmem_d, bool first, uint64_t* done_bar) {
+      const int st = (int)(g % S), sb = (int)(g % SB);
+      mbar_wait(&sm.a_full[st], (uint32_t)((g / S) & 1), 40);
+      mbar_wait(&sm.b_full[sb], (uint32_t)((g / SB) & 1), 41);
+      tc_fence_after();
+      const uint32_t a_big = ring_a_u + (uint32_t)st * kHAStage, a_small = a_big + kHTile;
+      const uint32_t b_big = ring_b_u + (uint32_t)sb * kHBStage, b_small = b_big + kHTile;
+      if (elect_one()) {
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t ko = (uint32_t)ks * 32u;   // 16 fp16 = 32 bytes along K inside the swizzled row
+          const uint64_t da_b = umma_desc_k128(a_big + ko), da_s = umma_desc_k128(a_small + ko);
+          const uint64_t db_b = umma_desc_k128(b_big + ko), db_s = umma_desc_k128(b_small + ko);
+          umma_f16(tmem_d, da_s, db_b, idesc, !(first && ks == 0));
+          umma_f16(tmem_d, da_b, db_s, idesc, true);
+          umma_f16(tmem_d, da_b, db_b, idesc, true);
+        }
+        umma_commit(&sm.a_empty[st]);
+        umma_commit(&sm.b_empty[sb]);
+        if (done_bar) umma_commit(done_bar);
+      }
+      __syncwarp();
+    };
+    auto gemm1 = [&](int it) {
+      const uint32_t d1 = tmem_u + (uint32_t)((it & 1) * kHHidden);
+      for (int kb = 0; kb < nkb1; ++kb) {
+        const int slots = min(2, K + 1 - 2 * kb);
+        block(g1(it, kb), 2 * slots, d1, kb == 0, kb == nkb1 - 1 ? &sm.d1_full[it & 1] : nullptr);
+      }
+    };
+    auto gemm2 = [&](int it) {
+      const int buf = it & 1;
+      mbar_wait(&sm.d2_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 42);  // epilogue-2 of item it-2 has drained D2[buf]
+      tc_fence_after();
+      const uint32_t d2 = tmem_u + (uint32_t)(2 * kHHidden + buf * kHHidden);
+      block(g2(it, 0), 4, d2, true, nullptr);
+      block(g2(it, 1), 4, d2, false, &sm.d2_full[buf]);
+    };
+    for (int it = 0; it < n; ++it) {
+      gemm1(it);
+      if (it > 0) gemm2(it - 1);
+    }
+    gemm2(n - 1);
+  } else if (warp == kLoadWarp) {
+    // ==================================================================================================== weight tiles
+    auto load = [&](uint32_t g, const uint8_t* tile) {
+      const int sb = (int)(g % SB);
+      mbar_wait(&sm.b_empty[sb], (uint32_t)(((g / SB) & 1) ^ 1), 60);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&sm.b_full[sb], kHBStage);
+        bulk_g2s(ring_b + (size_t)sb * kHBStage, tile, kHBStage, &sm.b_full[sb]);
+      }
+      __syncwarp();
+    };
+    for (int it = 0; it < n; ++it) {
+      for (int kb = 0; kb < nkb1; ++kb) load(g1(it, kb), w1p + (size_t)kb * kHBStage);
+      if (it > 0)
+        for (int j = 0; j < 2; ++j) load(g2(it - 1, j), w2p + (size_t)j * kHBStage);
+    }
+    for (int j = 0; j < 2; ++j) load(g2(n - 1, j), w2p + (size_t)j * kHBStage);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// arg-max keys -> best_index / lowest_cost (the plane depth at the arg-max, cost_volume.py:356-361)
+__global__ void cv_tch_finalize_kernel(const dtb200_cost_volume_params p, const unsigned long long* __restrict__ keys) {
+  const int HW = p.height * p.width;
+  const long long total = (long long)p.batch * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW), pix = (int)(i - (long long)b * HW);
+    const int idx = (int)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull));
+    if (p.best_index) p.best_index[i] = idx;
+    if (p.lowest_cost) p.lowest_cost[i] = plane_depth(p, b, idx, pix);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// weight preparation (once per weight version)
+// ---------------------------------------------------------------------------------------------------------------------
+// out[0] = 2^e, out[1] = 2^-e with e chosen so that max|w| * 2^e < 2^14 (one block)
+__global__ void cvh_scale_kernel(const float* __restrict__ w, int n, const float* __restrict__ extra, int n_extra, float* out) {
+  __shared__ float red[256];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  for (int i = threadIdx.x; i < n_extra; i += blockDim.x) m = fmaxf(m, fabsf(extra[i]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int e = 0;
+    if (red[0] > 0.f && isfinite(red[0])) {
+      int ex;
+      frexpf(red[0], &ex);   // max = f * 2^ex, f in [0.5, 1)
+      e = 14 - ex;
+    }
+    e = max(-100, min(100, e));
+    out[0] = ldexpf(1.f, e);
+    out[1] = ldexpf(1.f, -e);
+  }
+}
+
+// original feature index (reference channel order, mesh_hint_volume.py:343-367) of column j of slot s; -1 = zero padding,
+// -2 = the bias column
+__device__ __forceinline__ int cvh_feature_index(int K, int s, int j) {
+  const int meta = 16 * (K + 1);
+  if (s < K) {
+    if (j < 16) return 16 * s + j;
+    switch (j) {
+      case 16: return meta + s;                    // mask
+      case 17: return meta + K + s;                // source depth
+      case 18: return meta + 2 * K + 1 + s;        // dot product
+      case 19: return meta + 3 * K + 1 + s;        // ray angle
+      case 20: case 21: case 22: return meta + 4 * K + 4 + 3 * s + (j - 20);   // source ray
+      case 23: return meta + 7 * K + 4 + s;        // combined pose distance
+      case 24: return meta + 8 * K + 4 + s;        // R measure
+      case 25: return meta + 9 * K + 4 + s;        // t measure
+      default: return -1;
+    }
+  }
+  if (s == K) {
+    if (j < 16) return 16 * K + j;                 // current-view features
+    if (j == 16) return meta + 2 * K;              // plane depth
+    if (j >= 17 && j <= 19) return meta + 4 * K + 1 + (j - 17);   // current ray
+    if (j == 20) return -2;
+  }
+  return -1;
+}
+
+// W1 (128, 26K+20) + b1 -> nkb1 tiles [W_big | W_small], each [128 rows][64 fp16] SWIZZLE_128B K-major, scaled by scale[0]
+__global__ void cvh_pack_w1_kernel(const float* __restrict__ w1, const float* __restrict__ b1, uint8_t* __restrict__ packed, int K,
+                                   int nkb1, const float* __restrict__ scale) {
+  const int F = 26 * K + 20;
+  const long long total = (long long)nkb1 * kHHidden * 64;
+  const float sc = scale[0];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kb = (int)(i / (kHHidden * 64));
+    const int e = (int)(i - (long long)kb * kHHidden * 64);
+    const int row = e / 64, k = e % 64;
+    const int f = cvh_feature_index(K, 2 * kb + k / kHSlot, k % kHSlot);
+    float x = 0.f;
+    if (f >= 0) x = w1[(long long)row * F + f];
+    else if (f == -2) x = b1[row];
+    x *= sc;
+    const __half big = __float2half_rn(x);
+    const __half small = __float2half_rn(x - __half2float(big));
+    uint8_t* tile = packed + (size_t)kb * kHBStage;
+    *reinterpret_cast<__half*>(tile + sw128_offset_h(row, k)) = big;
+    *reinterpret_cast<__half*>(tile + kHTile + sw128_offset_h(row, k)) = small;
+  }
+}
+
+__global__ void cvh_pack_w2_kernel(const float* __restrict__ w2, uint8_t* __restrict__ packed, const float* __restrict__ scale) {
+  const long long total = 2LL * kHHidden * 64;
+  const float sc = scale[0];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kb = (int)(i / (kHHidden * 64));
+    const int e = (int)(i - (long long)kb * kHHidden * 64);
+    const int row = e / 64, k = e % 64;
+    const float x = w2[(long long)row * kHHidden + kb * 64 + k] * sc;
+    const __half big = __float2half_rn(x);
+    const __half small = __float2half_rn(x - __half2float(big));
+    uint8_t* tile = packed + (size_t)kb * kHBStage;
+    *reinterpret_cast<__half*>(tile + sw128_offset_h(row, k)) = big;
+    *reinterpret_cast<__half*>(tile + kHTile + sw128_offset_h(row, k)) = small;
+  }
+}
+
+static uint64_t cvh_weight_bytes(int K) { return kHHeaderBytes + (uint64_t)(cvh_nkb1(K) + 2) * kHBStage; }
+
+uint64_t cost_volume_tch_workspace_bytes(const dtb200_cost_volume_params& p) {
+  const uint64_t keys = ((uint64_t)p.batch * p.height * p.width * 8 + 255) / 256 * 256;
+  return cvh_weight_bytes(p.views) + keys;
+}
+
+int prepare_cost_volume_tch(const dtb200_cost_volume_params& p, cudaStream_t stream) {
+  if (!p.workspace || p.workspace_bytes < cost_volume_tch_workspace_bytes(p))
+    return fail(DTB200_ERR_INVALID, "cost volume (tch): workspace too small (dtb200_cost_volume_workspace_bytes)%s");
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p.workspace);
+  float* hdr = reinterpret_cast<float*>(ws);
+  const int K = p.views, nkb1 = cvh_nkb1(K);
+  cvh_scale_kernel<<<1, 256, 0, stream>>>(p.w1, kHHidden * (26 * K + 20), p.b1, kHHidden, hdr);
+  int rc = check_launch("cvh_scale_kernel");
+  if (rc != DTB200_OK) return rc;
+  cvh_scale_kernel<<<1, 256, 0, stream>>>(p.w2, kHHidden * kHHidden, nullptr, 0, hdr + 2);
+  rc = check_launch("cvh_scale_kernel");
+  if (rc != DTB200_OK) return rc;
+  cvh_pack_w1_kernel<<<64, 256, 0, stream>>>(p.w1, p.b1, ws + kHHeaderBytes, K, nkb1, hdr);
+  rc = check_launch("cvh_pack_w1_kernel");
+  if (rc != DTB200_OK) return rc;
+  cvh_pack_w2_kernel<<<32, 256, 0, stream>>>(p.w2, ws + kHHeaderBytes + (size_t)nkb1 * kHBStage, hdr + 2);
+  return check_launch("cvh_pack_w2_kernel");
+}
+
+static int g_cvh_sms[64] = {0};
+static std::once_flag g_cvh_once[64];
+static int g_cvh_variant = -1;   // producer warps: 8 or 16 (DTB200_CV_PRODUCERS, development switch)
+
+int launch_cost_volume_tch(const dtb200_cost_volume_params& p, cudaStream_t stream) {
+  if (!p.workspace || p.workspace_bytes < cost_volume_tch_workspace_bytes(p))
+    return fail(DTB200_ERR_INVALID, "cost volume (tch): workspace missing/too small (dtb200_cost_volume_workspace_bytes)%s");
+  if (!p.workspace_prepared) {
+    int rc = prepare_cost_volume_tch(p, stream);
+    if (rc != DTB200_OK) return rc;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  std::call_once(g_cvh_once[dev], [dev] {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    g_cvh_sms[dev] = sms > 0 ? sms : 148;
+    cudaFuncSetAttribute(cv_mlp_tch_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes);
+    cudaFuncSetAttribute(cv_mlp_tch_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes);
+    cudaFuncSetAttribute(cv_mlp_tch_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes);
+    cudaFuncSetAttribute(cv_mlp_tch_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBytes);
+    cudaGetLastError();
+    if (g_cvh_variant < 0) {
+      const char* e = getenv("DTB200_CV_PRODUCERS");
+      g_cvh_variant = (e && atoi(e) == 8) ? 8 : 16;
+    }
+  });
+  const int HW = p.height * p.width;
+  CvhWork wk;
+  wk.pix_groups = ceil_div(HW, kHPix);
+  wk.plane_chunks = ceil_div(p.planes, kHPlanes);
+  const long long total_items = (long long)p.batch * wk.pix_groups * wk.plane_chunks;
+  if (total_items > 0x3FFFFFFFLL) return fail(DTB200_ERR_UNSUPPORTED, "cost volume (tch): too many work items%s");
+  wk.total = (int)total_items;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p.workspace);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + cvh_weight_bytes(p.views));
+  cudaError_t e = cudaMemsetAsync(keys, 0, (size_t)p.batch * HW * 8, stream);
+  if (e != cudaSuccess) return fail(DTB200_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  const unsigned grid = (unsigned)(wk.total < g_cvh_sms[dev] ? wk.total : g_cvh_sms[dev]);
+  const bool hint = p.kind == DTB200_VOLUME_MLP_HINT;
+  if (g_cvh_variant == 8) {
+    constexpr int threads = (kHEpiWarps + 8 + 2) * 32;
+    if (hint) cv_mlp_tch_kernel<true, 8><<<grid, threads, kHSmemBytes, stream>>>(p, ws, keys, wk);
+    else cv_mlp_tch_kernel<false, 8><<<grid, threads, kHSmemBytes, stream>>>(p, ws, keys, wk);
+  } else {
+    constexpr int threads = (kHEpiWarps + 16 + 2) * 32;
+    if (hint) cv_mlp_tch_kernel<true, 16><<<grid, threads, kHSmemBytes, stream>>>(p, ws, keys, wk);
+    else cv_mlp_tch_kernel<false, 16><<<grid, threads, kHSmemBytes, stream>>>(p, ws, keys, wk);
+  }
+  int rc = check_launch("cv_mlp_tch_kernel");
+  if (rc != DTB200_OK) return rc;
+  const long long total = (long long)p.batch * HW;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cv_tch_finalize_kernel<<<blocks, 256, 0, stream>>>(p, keys);
+  return check_launch("cv_tch_finalize_kernel");
+}
+
+}  // namespace dtb200

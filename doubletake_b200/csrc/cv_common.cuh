@@ -118,6 +118,26 @@ __device__ __forceinline__ float4 sample_apply(const float* __restrict__ src_vie
   return acc;
 }
 
+// Branch-free form of sample_apply for the tensor-core kernels: the four taps are loaded by predicated instructions (all
+// in flight together) and an out-of-image tap contributes fma(0, 0, acc) = acc, i.e. exactly nothing (the weight is zeroed
+// too: NaN coordinates fail every range test but leave NaN weights).  Same FMA order as sample_apply.
+__device__ __forceinline__ float4 sample_apply_nb(const float* __restrict__ src_view, int q, const SampleSetup& s, int W) {
+  const float4* base = reinterpret_cast<const float4*>(src_view + s.off + q * 4);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool v0 = s.mask & 1, v1 = s.mask & 2, v2 = s.mask & 4, v3 = s.mask & 8;
+  const float4 t0 = v0 ? __ldg(base) : z;
+  const float4 t1 = v1 ? __ldg(base + kC / 4) : z;
+  const float4 t2 = v2 ? __ldg(base + (W * kC) / 4) : z;
+  const float4 t3 = v3 ? __ldg(base + ((W + 1) * kC) / 4) : z;
+  const float w0 = v0 ? s.w[0] : 0.f, w1 = v1 ? s.w[1] : 0.f, w2 = v2 ? s.w[2] : 0.f, w3 = v3 ? s.w[3] : 0.f;
+  float4 acc;
+  acc.x = DT_FMA(t3.x, w3, DT_FMA(t2.x, w2, DT_FMA(t1.x, w1, DT_FMA(t0.x, w0, 0.f))));
+  acc.y = DT_FMA(t3.y, w3, DT_FMA(t2.y, w2, DT_FMA(t1.y, w1, DT_FMA(t0.y, w0, 0.f))));
+  acc.z = DT_FMA(t3.z, w3, DT_FMA(t2.z, w2, DT_FMA(t1.z, w1, DT_FMA(t0.z, w0, 0.f))));
+  acc.w = DT_FMA(t3.w, w3, DT_FMA(t2.w, w2, DT_FMA(t1.w, w1, DT_FMA(t0.w, w0, 0.f))));
+  return acc;
+}
+
 __device__ __forceinline__ float4 sample_quad(const float* __restrict__ src_view, int q, float u, float v, int H, int W,
                                               float invW, float invH) {
   return sample_apply(src_view, q, sample_setup(u, v, H, W, invW, invH), W);
@@ -166,5 +186,7 @@ __device__ __forceinline__ void write_masks(const dtb200_cost_volume_params& p, 
 }
 
 __device__ __forceinline__ float leaky01(float x) { return x > 0.f ? x : DT_MUL(x, 0.01f); }
+// the same function in two instructions (slope < 1: max(x, 0.01 x) picks x for x > 0 and 0.01 x otherwise; NaN stays NaN)
+__device__ __forceinline__ float leaky01_fast(float x) { return fmaxf(x, DT_MUL(x, 0.01f)); }
 
 }  // namespace dtb200

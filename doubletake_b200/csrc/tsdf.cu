@@ -46,9 +46,12 @@ __device__ __forceinline__ bool nearest_index(float g, int size, int semantics, 
     i = hr(DT_MUL(i, (float)size));
     i = hr(DT_SUB(i, 1.f));
     i = hr(DT_DIV(i, 2.f));
-  } else {
-    // GridSampler.cuh: `coord + 1.f` promotes to fp32; the result is stored back into an fp16 scalar_t
+  } else if (semantics == DTB200_TSDF_SEMANTICS_ATEN_CUDA_HALF_INDEX) {
+    // GridSampler.cuh with a scalar_t index: `coord + 1.f` promotes to fp32; the result is stored back into an fp16 scalar
     i = hr(DT_DIV(DT_SUB(DT_MUL(DT_ADD(g, 1.f), (float)size), 1.f), 2.f));
+  } else {
+    // GridSampler.cu with opmath_t (fp32) coordinates: the index never goes back to fp16
+    i = DT_DIV(DT_SUB(DT_MUL(DT_ADD(g, 1.f), (float)size), 1.f), 2.f);
   }
   float n = rintf(i);  // nearbyint, ties to even
   if (semantics == DTB200_TSDF_SEMANTICS_ATEN_CPU) {
@@ -221,7 +224,8 @@ extern "C" int dtb200_tsdf_integrate(const dtb200_tsdf_integrate_params* p, dtb2
       return fail(DTB200_ERR_INVALID, "tsdf_integrate: volume dims must be positive multiples of 8 (TSDF.VOX_MOD), got %s%lld", "",
                   (long long)p->dims[a]);
   if (p->img_h < 1 || p->img_w < 1) return fail(DTB200_ERR_INVALID, "tsdf_integrate: bad image size%s");
-  if (p->semantics != DTB200_TSDF_SEMANTICS_ATEN_CPU && p->semantics != DTB200_TSDF_SEMANTICS_ATEN_CUDA)
+  if (p->semantics != DTB200_TSDF_SEMANTICS_ATEN_CPU && p->semantics != DTB200_TSDF_SEMANTICS_ATEN_CUDA &&
+      p->semantics != DTB200_TSDF_SEMANTICS_ATEN_CUDA_HALF_INDEX)
     return fail(DTB200_ERR_INVALID, "tsdf_integrate: unknown semantics%s");
   for (int b = 0; b < p->num_frames; ++b)
     if (!p->frames[b].depth) return fail(DTB200_ERR_INVALID, "tsdf_integrate: frame %s%lld has no depth map", "", (long long)b);

@@ -63,9 +63,12 @@ int dtb200_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w
 #define DTB200_VOLUME_MLP_HINT 2
 
 /* math modes: EXACT = fp32 FMA in the reference operation order (bit-reproducible, CUDA cores);
- * TC3X = tcgen05 tensor cores with the 3xTF32 split (fp32-class accuracy, ~2^-21 per product) */
+ * TC3X = tcgen05 tensor cores with the 3xTF32 split (fp32-class accuracy, ~2^-21 per product);
+ * TCH  = tcgen05 kind::f16 with a 2-term fp16 split of both operands (big + small, three MMAs per product at twice the
+ *        TF32 rate and half the operand bytes; the same ~2^-21 accuracy class) -- the default of the benchmark */
 #define DTB200_MATH_EXACT 0
 #define DTB200_MATH_TC3X 1
+#define DTB200_MATH_TCH 2
 
 typedef struct {
   int32_t kind;          /* DTB200_VOLUME_* */
@@ -99,9 +102,10 @@ typedef struct {
   int32_t* best_index;  /* (B,H,W) arg-max plane index; may be NULL */
   uint8_t* mask_views;  /* (B,K,H,W) last-plane depth-valid & in-bounds per view; may be NULL */
   uint8_t* mask_any;    /* (B,H,W) any_k(depth-valid) & any_k(in-bounds) on the last plane; may be NULL */
-  /* math = TC3X: device scratch holding the MLP weights re-tiled for the tensor cores (size from
-   * dtb200_cost_volume_workspace_bytes).  dtb200_cost_volume_prepare fills it; set workspace_prepared = 1 to reuse it on
-   * later calls with the same weights (otherwise every call re-tiles first).  NULL / 0 for the other modes. */
+  /* math = TC3X / TCH: device scratch holding the MLP weights re-tiled for the tensor cores (TCH: plus 8 bytes per pixel
+   * of arg-max keys), size from dtb200_cost_volume_workspace_bytes.  dtb200_cost_volume_prepare fills the weight part;
+   * set workspace_prepared = 1 to reuse it on later calls with the same weights (otherwise every call re-tiles first).
+   * NULL / 0 for EXACT. */
   void* workspace;
   uint64_t workspace_bytes;
   int32_t workspace_prepared;
@@ -222,7 +226,10 @@ int dtb200_exp(const float* src, float* dst, uint64_t count, dtb200_stream_t str
  * ---------------------------------------------------------------------------------------------------------- */
 #define DTB200_TSDF_MAX_FRAMES 8
 #define DTB200_TSDF_SEMANTICS_ATEN_CPU 0  /* fp16 grid_sample as ATen's CPU build evaluates it (pinned by the fixtures) */
-#define DTB200_TSDF_SEMANTICS_ATEN_CUDA 1 /* ... as ATen's CUDA build does (fp32 un-normalise, saturating index cast) */
+#define DTB200_TSDF_SEMANTICS_ATEN_CUDA 1 /* ... as ATen's CUDA build does: index arithmetic in fp32 (opmath_t), saturating
+                                             index cast -- pinned against torch 2.11 CUDA on the GPU box */
+#define DTB200_TSDF_SEMANTICS_ATEN_CUDA_HALF_INDEX 2 /* older ATen CUDA builds: the un-normalised index is rounded to fp16
+                                                        before nearbyint (restated from source, not executable here) */
 
 typedef struct dtb200_tsdf_frame {
   const void* depth;       /* fp16 (img_h, img_w) depth map; <= 0 = no measurement */

@@ -81,15 +81,19 @@ def nearest_sample_h(depth_hw, px, py, semantics="cpu"):
     * ``"cpu"`` (what the golden fixtures pin: the reference executed on CPU): ``((g + 1) * size - 1) / 2`` in c10::Half
       arithmetic, one fp16 rounding per operation; a NaN / +-inf index converts to integer 0 (x86 build), i.e. such
       voxels read row / column 0 instead of the zero padding.
-    * ``"cuda"`` (ATen GridSampler.cu, not executable here -> unpinned): the same formula in fp32 (``coord + 1.f`` promotes),
-      rounded to fp16 once on return; the float -> int conversion saturates, so +-inf is out of bounds and NaN is 0."""
+    * ``"cuda"`` (ATen GridSampler.cu with opmath_t coordinates; pinned on the GPU box against torch's own CUDA ops through
+      oracle_tsdf_torch.py): the same formula in fp32, never rounded back to fp16; the float -> int conversion saturates,
+      so +-inf is out of bounds and NaN is 0.
+    * ``"cuda_half_index"`` (older ATen CUDA builds with a scalar_t index; restated from source, unpinned): as "cuda" but
+      the un-normalised index is rounded to fp16 once before nearbyint."""
     H, W = depth_hw.shape
 
     def unnormalize(g, size):
         if semantics == "cpu":
             i = h(f(h(f(h(f(g) + F32(1))) * F32(size))) - F32(1))
             return f(h(f(i) / F32(2)))
-        return f(h((((f(g) + F32(1)) * F32(size)).astype(F32) - F32(1)).astype(F32) / F32(2)))
+        i32 = ((((f(g) + F32(1)) * F32(size)).astype(F32) - F32(1)).astype(F32) / F32(2)).astype(F32)
+        return f(h(i32)) if semantics == "cuda_half_index" else i32
 
     with np.errstate(invalid="ignore", over="ignore"):
         xn, yn = np.rint(unnormalize(px, W)), np.rint(unnormalize(py, H))  # nearbyint: ties to even

@@ -21,7 +21,8 @@ def run_case(cfg, math):
     fam = "efficientnet" if cfg.prior_ch[0] == 24 else "resnet18d"
     opts = dt.HotPathOptions(image_encoder_name=fam, depth_decoder_name=cfg.decoder, matching_num_depth_bins=cfg.planes,
                              model_num_views=cfg.num_src + 1, image_height=cfg.image_h, image_width=cfg.image_w)
-    model = dt.DepthModelCVHint(opts, math=math, volume_math=math)
+    conv_math, volume_math = (math.split("+") + [math])[:2]
+    model = dt.DepthModelCVHint(opts, math=conv_math, volume_math=volume_math)
     shapes = {k: tuple(v.shape) for k, v in model.named_parameters()}
     sd = syn.seeded_state_dict(shapes, 2024, 1.3)
     model.load_state_dict(sd, strict=False)
@@ -65,7 +66,7 @@ def check(out, ref, cfg, tag="tc3x"):
         assert float(mism.float().mean()) < 1e-3, int(mism.sum())
 
 
-@pytest.mark.parametrize("math", ["tc3x", "exact"])
+@pytest.mark.parametrize("math", ["tc3x", "exact", "tc3x+tch"])
 def test_cfg2_full_frame_matches_oracle(math):
     """BASELINE cfg 2 (the bench workload): 640x480 image, 120x160x16 features, 64 planes, 7 views, hint, DepthDecoderPP."""
     cfg = syn.CONFIGS["cfg2"]

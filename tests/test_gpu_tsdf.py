@@ -84,12 +84,13 @@ def test_more_frames_than_one_launch_holds():
     assert np.array_equal(bits(vol.tsdf_weights), bits(ref["tsdf_weights"]))
 
 
-def test_aten_cuda_semantics_match_their_restatement():
+@pytest.mark.parametrize("sem", ["cuda", "cuda_half_index"])
+def test_aten_cuda_semantics_match_their_restatement(sem):
     fx = hp.load("tsdf_near")
-    vol, _ = run_case(fx, semantics="aten_cuda")
+    vol, _ = run_case(fx, semantics="aten_" + sem)
     ref = ot.volume_from_bounds(case_bounds(fx), float(fx["voxel_size"]))
     ot.integrate_depth(ref, fx["depth"], fx["cam_T_world"], fx["K"], min_depth=0.5, max_depth=float(fx["max_depth"]),
-                       semantics="cuda")
+                       semantics=sem)
     assert np.array_equal(bits(vol.tsdf_values), bits(ref["tsdf_values"]))
     assert np.array_equal(bits(vol.tsdf_weights), bits(ref["tsdf_weights"]))
     assert not np.array_equal(bits(vol.tsdf_weights), bits(fx["weights"]))  # the pinned build differs on overflowed pixels
@@ -110,6 +111,7 @@ def test_aten_cuda_semantics_match_torch_cuda_ops(name):
     fx = hp.load(name)
     seed, nf, ih, iw, fb, with_mask, ext = [int(v) for v in fx["meta"]]
     vol, _ = run_case(fx, semantics="aten_cuda")
+    legacy, _ = run_case(fx, semantics="aten_cuda_half_index")
     coords = torch.from_numpy(fx["voxel_coords"]).cuda()
     values = -torch.ones(coords.shape[1:], dtype=torch.float16, device="cuda")
     weights = torch.zeros(coords.shape[1:], dtype=torch.float16, device="cuda")
@@ -123,7 +125,9 @@ def test_aten_cuda_semantics_match_torch_cuda_ops(name):
     touched = int((weights > 0).sum())
     dv = int((bits(vol.tsdf_values) != bits(values)).sum())
     dw = int((bits(vol.tsdf_weights) != bits(weights)).sum())
-    print(f"[tsdf aten_cuda vs torch CUDA] {name}: touched {touched}, value bits differ {dv}, weight bits differ {dw}")
+    lv = int((bits(legacy.tsdf_values) != bits(values)).sum())
+    print(f"[tsdf aten_cuda vs torch {torch.__version__} CUDA] {name}: touched {touched}, value bits differ {dv}, weight bits "
+          f"differ {dw} (half-index variant: {lv} values differ)")
     assert touched > 10000 and dv <= touched // 1000 and dw <= touched // 1000, (touched, dv, dw)
 
 

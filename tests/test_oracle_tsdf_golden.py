@@ -51,17 +51,20 @@ def test_oracle_sampling_is_bit_exact(name):
 
 def test_nonfinite_pixel_coordinates_follow_the_pinned_build():
     """tsdf_near holds voxels whose projected pixel overflows fp16: ATen's CPU build reads row / column 0 there (pinned),
-    its CUDA build reads the zero padding -- the two semantics must differ on exactly such voxels and nowhere else."""
+    its CUDA builds read the zero padding -- the half-index CUDA semantics must differ from the CPU's on exactly such voxels
+    and nowhere else; the fp32-index CUDA semantics (opmath_t coordinates) additionally moves every voxel whose fp16-rounded
+    index falls on the other side of a .5 boundary."""
     fx = hp.load("tsdf_near")
     res = {}
-    for sem in ("cpu", "cuda"):
+    for sem in ("cpu", "cuda_half_index", "cuda"):
         vol = ot.volume_from_bounds(case_bounds(fx), float(fx["voxel_size"]))
         ot.integrate_depth(vol, fx["depth"], fx["cam_T_world"], fx["K"], min_depth=float(fx["min_depth"]),
                            max_depth=float(fx["max_depth"]), semantics=sem)
         res[sem] = vol["tsdf_weights"].copy()
     assert np.array_equal(bits(res["cpu"]), bits(fx["weights"]))
-    diff = int((bits(res["cpu"]) != bits(res["cuda"])).sum())
+    diff = int((bits(res["cpu"]) != bits(res["cuda_half_index"])).sum())
     assert 0 < diff < 100
+    assert int((bits(res["cuda"]) != bits(res["cuda_half_index"])).sum()) > 0
 
 
 @pytest.mark.parametrize("name", CASES)
