@@ -303,7 +303,8 @@ def run_b200(args):
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.math == "exact" else "f32 via 3xTF32 (tf32 big/small split, fp32 accumulate)",
+            "dtype": {"exact": "f32", "tc3x": "f32 via 3xTF32 (tf32 big/small split, fp32 accumulate)",
+                      "tch": "f32 via 2-term fp16 split (big + small/2048, three kind::f16 MMAs per product, fp32 accumulate)"}[args.math],
             "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC, "math": args.math, "volume_math": volume_math, "frames_per_step": frames_per_step,
                        "l2": "256 MiB L2 flush between timed steps (outside the per-step event pairs); 4 rotating input sets",
@@ -387,12 +388,16 @@ def kernel_rooflines(model, dev_sets, cfg, flush, L, reps=5):
             "ms_per_launch": round(conv_ms / n_conv, 5), "launches_per_step": n_conv, "ms_all_launches": round(conv_ms, 4),
             "algorithmic_flops": conv_flops, "peak_source": peaks["src"] + " bf16 sustained"},
     }
-    if model.math == "tc3x":
-        # context for `frac`: an fp32-accurate tensor-core path issues 3 TF32 MMAs per product and TF32 runs at half the
-        # bf16 rate, so its ceiling is peak / 6 -- reported next to the contract's frac-of-bf16-peak, never instead of it
-        for e in entries.values():
-            e["ceiling_3xtf32"] = round(tens_peak / 6.0, 1)
-            e["frac_of_3xtf32_ceiling"] = round(e["achieved"] / (tens_peak / 6.0), 4)
+    # context for `frac`: an fp32-accurate tensor-core path issues 3 MMAs per product -- TF32 ones at half the bf16 rate
+    # (ceiling = peak / 6) or, with the fp16 split, f16 ones at the full rate (ceiling = peak / 3); reported next to the
+    # contract's frac-of-bf16-peak, never instead of it
+    maths = {"conv_stack": model.math, "cost_volume_mlp_hint": model.volume_math}
+    for name, e in entries.items():
+        div = {"tc3x": 6.0, "tch": 3.0}.get(maths[name])
+        if div:
+            e["split_ceiling"] = round(tens_peak / div, 1)
+            e["frac_of_split_ceiling"] = round(e["achieved"] / (tens_peak / div), 4)
+            e["split"] = {"tc3x": "3xTF32", "tch": "2-term fp16, 3 MMAs"}[maths[name]]
     dom = "conv_stack" if conv_ms >= cv_ms else "cost_volume_mlp_hint"
     d = dict(entries[dom])
     d["kernel"] = dom
@@ -503,8 +508,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--math", default="tc3x", choices=["exact", "tc3x"],
-                    help="tc3x: tcgen05 tensor cores with the 3xTF32 split (fp32-class, parity-green); exact: fp32 CUDA cores")
+    ap.add_argument("--math", default="tch", choices=["exact", "tc3x", "tch"],
+                    help="tch: tcgen05 kind::f16 with the 2-term fp16 split of activations and weights (fp32-class, parity-green, "
+                         "default); tc3x: 3xTF32 split; exact: fp32 CUDA cores")
     ap.add_argument("--volume-math", default=None, choices=["exact", "tc3x", "tch"],
                     help="cost-volume MLP arithmetic; default: tch (kind::f16, 2-term fp16 split) unless --math exact")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -80,6 +80,8 @@ SYMBOLS = {
     "dtb200_launch_count": (C.c_uint64, []),
     "dtb200_nchw_to_nhwc": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),
     "dtb200_nhwc_to_nchw": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),
+    "dtb200_nchw_to_split16": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),
+    "dtb200_split16_to_nchw": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),
     "dtb200_cost_volume_workspace_bytes": (C.c_uint64, [C.POINTER(CostVolumeParams)]),
     "dtb200_cost_volume_prepare": (C.c_int, [C.POINTER(CostVolumeParams), fp]),
     "dtb200_cost_volume": (C.c_int, [C.POINTER(CostVolumeParams), fp]),
@@ -170,6 +172,20 @@ def nhwc_to_nchw(x, out=None):
     if out is None:
         out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
     check(lib().dtb200_nhwc_to_nchw(ptr(x), ptr(out), n, c, h, w, stream()))
+    return out
+
+
+def nchw_to_split16(x, out):
+    """(N,C,H,W) fp32 CUDA -> split16 (N,H,W,2,C) fp16 written into `out` (any dense buffer of N*H*W*C*4 bytes)."""
+    x = f32(x)
+    n, c, h, w = x.shape
+    check(lib().dtb200_nchw_to_split16(ptr(x), ptr(out), n, c, h, w, stream()))
+    return out
+
+
+def split16_to_nchw(buf, n, c, h, w):
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=buf.device)
+    check(lib().dtb200_split16_to_nchw(ptr(buf), ptr(out), n, c, h, w, stream()))
     return out
 
 

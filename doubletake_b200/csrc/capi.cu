@@ -15,6 +15,13 @@ uint64_t packed_floats_tc(int out_c, int num_src, const int32_t* src_c, int ksiz
 uint64_t conv_tc_workspace_bytes(const dtb200_conv_params& p, int in_c_total);                           // conv_tc.cu
 int launch_resample_copy(const dtb200_conv_params& p, cudaStream_t stream);                              // conv_tc.cu
 int conv_tc_debug_set(int flags);                                                                        // conv_tc.cu
+int launch_conv_tch(const dtb200_conv_params& p, int in_c_total, cudaStream_t stream);                   // conv_tch.cu
+int launch_pack_tch(const float* oihw, float* packed, int out_c, int num_src, const int32_t* src_c, int ksize,
+                    cudaStream_t s);                                                                     // conv_tch.cu
+uint64_t packed_floats_tch(int out_c, int num_src, const int32_t* src_c, int ksize);                     // conv_tch.cu
+uint64_t conv_tch_workspace_bytes(const dtb200_conv_params& p);                                          // conv_tch.cu
+int launch_resample_copy_h(const dtb200_conv_params& p, cudaStream_t stream);                            // conv_tch.cu
+int launch_split16_transpose(const void* src, void* dst, int n, int c, int hw, bool to_split, cudaStream_t stream);  // conv_tch.cu
 
 // (N,C,H,W) <-> (N,H,W,C): 32x32 smem tile transpose of the (C, H*W) matrix of each sample.
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
@@ -106,6 +113,14 @@ extern "C" int dtb200_nhwc_to_nchw(const float* src, float* dst, int n, int c, i
   return transpose(src, dst, n, h * w, c, (cudaStream_t)stream);
 }
 
+extern "C" int dtb200_nchw_to_split16(const float* src, void* dst, int n, int c, int h, int w, dtb200_stream_t stream) {
+  if (c % 8 != 0) return fail(DTB200_ERR_INVALID, "nchw_to_split16: channels must be a multiple of 8, got %s%lld", "", c);
+  return launch_split16_transpose(src, dst, n, c, h * w, true, (cudaStream_t)stream);
+}
+extern "C" int dtb200_split16_to_nchw(const void* src, float* dst, int n, int c, int h, int w, dtb200_stream_t stream) {
+  return launch_split16_transpose(src, dst, n, c, h * w, false, (cudaStream_t)stream);
+}
+
 extern "C" int dtb200_relative_poses(const float* src_cam_T_world, const float* src_world_T_cam,
                                      const float* cur_cam_T_world, const float* cur_world_T_cam,
                                      float* src_cam_T_cur_cam, float* cur_cam_T_src_cam, int batch, int views,
@@ -136,6 +151,7 @@ extern "C" uint64_t dtb200_packed_conv_weight_floats_srcs(int32_t math, int32_t 
                                                           int32_t ksize) {
   if (!src_c || num_src < 1 || num_src > DTB200_CONV_MAX_SRC) return 0;
   if (math == DTB200_MATH_TC3X) return packed_floats_tc(out_c, num_src, src_c, ksize);
+  if (math == DTB200_MATH_TCH) return packed_floats_tch(out_c, num_src, src_c, ksize);
   uint64_t in_c = 0;
   for (int s = 0; s < num_src; ++s) in_c += src_c[s];
   return (uint64_t)out_c * in_c * ksize * ksize;
@@ -156,12 +172,15 @@ extern "C" int dtb200_pack_conv_weight_srcs(int32_t math, const float* oihw, flo
     in_c += src_c[s];
   }
   if (math == DTB200_MATH_TC3X) return launch_pack_tc(oihw, packed, out_c, num_src, src_c, ksize, (cudaStream_t)stream);
+  if (math == DTB200_MATH_TCH) return launch_pack_tch(oihw, packed, out_c, num_src, src_c, ksize, (cudaStream_t)stream);
   if (math == DTB200_MATH_EXACT) return launch_pack_simt(oihw, packed, out_c, in_c, ksize, (cudaStream_t)stream);
   return fail(DTB200_ERR_INVALID, "pack_conv_weight: unknown math mode%s");
 }
 
 extern "C" uint64_t dtb200_conv_workspace_bytes(const dtb200_conv_params* p) {
-  if (!p || p->math != DTB200_MATH_TC3X || p->ksize == 0) return 0;
+  if (!p || p->ksize == 0) return 0;
+  if (p->math == DTB200_MATH_TCH) return conv_tch_workspace_bytes(*p);
+  if (p->math != DTB200_MATH_TC3X) return 0;
   int total = 0;
   for (int s = 0; s < p->num_src && s < DTB200_CONV_MAX_SRC; ++s) total += p->src_c[s];
   return conv_tc_workspace_bytes(*p, total);
@@ -169,11 +188,13 @@ extern "C" uint64_t dtb200_conv_workspace_bytes(const dtb200_conv_params* p) {
 
 extern "C" int dtb200_conv2d(const dtb200_conv_params* p, dtb200_stream_t stream) {
   if (!p) return fail(DTB200_ERR_INVALID, "conv: null params%s");
-  if (p->ksize == 0) return launch_resample_copy(*p, (cudaStream_t)stream);
+  if (p->ksize == 0)
+    return p->math == DTB200_MATH_TCH ? launch_resample_copy_h(*p, (cudaStream_t)stream) : launch_resample_copy(*p, (cudaStream_t)stream);
   int total = 0;
   int rc = conv_total_in_c(*p, total);
   if (rc != DTB200_OK) return rc;
   if (p->math == DTB200_MATH_TC3X) return launch_conv_tc(*p, total, (cudaStream_t)stream);
+  if (p->math == DTB200_MATH_TCH) return launch_conv_tch(*p, total, (cudaStream_t)stream);
   if (p->math == DTB200_MATH_EXACT) return launch_conv_simt(*p, total, (cudaStream_t)stream);
   return fail(DTB200_ERR_INVALID, "conv: unknown math mode%s");
 }

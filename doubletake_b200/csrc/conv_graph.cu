@@ -19,6 +19,7 @@ namespace dtb200 {
 
 uint64_t conv_tc_workspace_bytes(const dtb200_conv_params& p, int in_c_total);  // conv_tc.cu
 int conv_tc_init();                                                             // conv_tc.cu
+int conv_tch_init();                                                            // conv_tch.cu
 
 namespace {
 
@@ -50,10 +51,8 @@ OpAccess access_of(const dtb200_conv_params& p) {
   const uint64_t out_bytes = (uint64_t)p.batch * p.out_h * p.out_w * p.out_c * sizeof(float);
   if (p.residual && p.ksize != 0) a.reads[a.num_reads++] = range_of(p.residual, out_bytes);
   if (p.dst) a.writes[a.num_writes++] = range_of(p.dst, out_bytes);
-  if (p.workspace && p.ksize != 0 && p.math == DTB200_MATH_TC3X) {
-    int in_c = 0;
-    for (int s = 0; s < p.num_src && s < DTB200_CONV_MAX_SRC; ++s) in_c += p.src_c[s];
-    const uint64_t ws = conv_tc_workspace_bytes(p, in_c);
+  if (p.workspace && p.ksize != 0) {
+    const uint64_t ws = dtb200_conv_workspace_bytes(&p);   // split-K scratch of the tensor-core modes
     if (ws) a.writes[a.num_writes++] = range_of(p.workspace, ws);
   }
   return a;
@@ -205,6 +204,7 @@ extern "C" int dtb200_conv_graph_create(const dtb200_conv_params* ops, int32_t c
   *out = nullptr;
   Schedule sc = analyse(ops, count, max_lanes);
   conv_tc_init();  // resolve driver entry points / device attributes before capture starts
+  conv_tch_init();
 
   std::vector<cudaStream_t> lanes(sc.lanes_used, nullptr);
   std::vector<cudaEvent_t> done(count, nullptr), joined(sc.lanes_used, nullptr);

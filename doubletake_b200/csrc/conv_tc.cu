@@ -133,9 +133,9 @@ struct RoleProf {
   long long t0 = 0, waited = 0;
   int n = 0;
 };
-__device__ __forceinline__ void prof_wait(uint64_t* bar, uint32_t parity, bool on, RoleProf& pr) {
+__device__ __forceinline__ void prof_wait(uint64_t* bar, uint32_t parity, bool on, RoleProf& pr, uint32_t sleep_ns = 0) {
   if (!on) {
-    mbar_wait(bar, parity);
+    mbar_wait(bar, parity, 0, sleep_ns);
     return;
   }
   const long long a = clock64();
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
         dst = p.dst + m * p.out_c + n_base;
         res = p.residual ? p.residual + m * p.out_c + n_base : nullptr;
       }
-      prof_wait(&acc_full[buf], (use >> 1) & 1, prof, pr);
+      prof_wait(&acc_full[buf], (use >> 1) & 1, prof, pr, 128);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(buf * Cfg::kAccCols) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
 #pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
         if (split_all || (stage & 1) == group) {
-          prof_wait(&raw_full[stage], phase, prof, pr);
+          prof_wait(&raw_full[stage], phase, prof, pr, 32);
           if (prof && st == 0) pr2.waited += clock64() - stamp[stage], ++pr2.n;  // TMA issue -> box landed and seen
           if (!(dbg & 2)) {
             // all loads first (explicit ld.shared: the generic-pointer form serialises load -> store -> load on possible
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const dtb200_conv_
       klayout_decode(kl, kb_begin, tap, src, c0);
       int ky = tap / p.ksize, kx = tap - ky * p.ksize;
       for (int kb = 0; kb < num_kb; ++kb) {
-        prof_wait(&empty[stage], phase ^ 1, prof, pr);
+        prof_wait(&empty[stage], phase ^ 1, prof, pr, 32);
         if (prof && warp == kLoadWarp && lane == 0) {
           const long long now = clock64();
           if (stamp[S + stage] != 0) pr2.waited += now - stamp[S + stage], ++pr2.n;  // commit issued -> loader sees `empty`
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const dtb200_
       const int n_base = n_tile * BN;
       float* dst = p.dst + m * p.out_c + n_base;
       const float* res = p.residual ? p.residual + m * p.out_c + n_base : nullptr;
-      mbar_wait(&acc_full[buf], (use >> 1) & 1, 1);
+      mbar_wait(&acc_full[buf], (use >> 1) & 1, 1, 128);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(buf * Cfg::kAccCols) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const dtb200_
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x) {
 #pragma unroll 1
       for (int ch = 0; ch < chunks; ++ch) {
-        mbar_wait(&raw_full[stage], phase, 2);
+        mbar_wait(&raw_full[stage], phase, 2, 32);
         const uint32_t raw_u = ring_u + (uint32_t)(stage * kHaloAStageBytes);
         float4 v[12];
 #pragma unroll
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const dtb200_
       decode(item, bb, y0, x0, n_tile);
       int src = 0, c0 = 0;
       for (int ch = 0; ch < chunks; ++ch) {
-        mbar_wait(&a_empty[stage], phase ^ 1, 6);
+        mbar_wait(&a_empty[stage], phase ^ 1, 6, 64);
         if (elect_one()) {
           mbar_arrive_expect_tx(&raw_full[stage], kHaloPatchBytes);
           tma_load_4d(ring_a + stage * kHaloAStageBytes, &maps.m[src], c0, x0 - 1, y0 - 1, bb, &raw_full[stage]);
@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const dtb200_
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.weight) + (size_t)n_tile * wk.num_kb_total * Cfg::kBBytes;
       for (int ch = 0; ch < chunks; ++ch) {
         for (int g = 0; g < 9 / kTB; ++g) {
-          mbar_wait(&b_empty[stage], phase ^ 1, 7);
+          mbar_wait(&b_empty[stage], phase ^ 1, 7, 32);
           if (elect_one()) {
             mbar_arrive_expect_tx(&b_full[stage], Cfg::kBStageBytes);
 #pragma unroll

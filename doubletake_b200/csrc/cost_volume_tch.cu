@@ -189,11 +189,11 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
 
     auto epi1 = [&](int it) {
       const int buf = it & 1;
-      mbar_wait(&sm.d1_full[buf], (it >> 1) & 1, 20);
+      mbar_wait(&sm.d1_full[buf], (it >> 1) & 1, 20, 64);
       tc_fence_after();
       const uint32_t g = g2(it, half);
       const int st = (int)(g % S);
-      mbar_wait(&sm.a_empty[st], (uint32_t)(((g / S) & 1) ^ 1), 21);
+      mbar_wait(&sm.a_empty[st], (uint32_t)(((g / S) & 1) ^ 1), 21, 32);
       const uint32_t a_big = ring_u + (uint32_t)st * kHAStage;
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
 
     auto epi2 = [&](int it) {
       const int buf = it & 1;
-      mbar_wait(&sm.d2_full[buf], (it >> 1) & 1, 22);
+      mbar_wait(&sm.d2_full[buf], (it >> 1) & 1, 22, 64);
       tc_fence_after();
       float s = 0.f;
 #pragma unroll 1
@@ -360,8 +360,8 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
         const bool has_b = kb0 + 1 < nkb1;
         const uint32_t gA = g1(it, kb0), gB = gA + 1;
         const int stA = (int)(gA % S), stB = (int)(gB % S);
-        mbar_wait(&sm.a_empty[stA], (uint32_t)(((gA / S) & 1) ^ 1), 10);
-        if (has_b) mbar_wait(&sm.a_empty[stB], (uint32_t)(((gB / S) & 1) ^ 1), 11);
+        mbar_wait(&sm.a_empty[stA], (uint32_t)(((gA / S) & 1) ^ 1), 10, 64);
+        if (has_b) mbar_wait(&sm.a_empty[stB], (uint32_t)(((gB / S) & 1) ^ 1), 11, 64);
         const uint32_t baseA = ring_u + (uint32_t)stA * kHAStage, baseB = ring_u + (uint32_t)stB * kHAStage;
         const int my_slot = 4 * pass + q;   // the slot whose per-(row, view) scalar work this lane does
 #pragma unroll
@@ -469,8 +469,8 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
     const uint32_t ring_a_u = smem_u32(ring_a), ring_b_u = smem_u32(ring_b);
     auto block = [&](uint32_t g, int ksteps, uint32_t tmem_d, bool first, uint64_t* done_bar) {
       const int st = (int)(g % S), sb = (int)(g % SB);
-      mbar_wait(&sm.a_full[st], (uint32_t)((g / S) & 1), 40);
-      mbar_wait(&sm.b_full[sb], (uint32_t)((g / SB) & 1), 41);
+      mbar_wait(&sm.a_full[st], (uint32_t)((g / S) & 1), 40, 20);
+      mbar_wait(&sm.b_full[sb], (uint32_t)((g / SB) & 1), 41, 20);
       tc_fence_after();
       const uint32_t a_big = ring_a_u + (uint32_t)st * kHAStage, a_small = a_big + kHTile;
       const uint32_t b_big = ring_b_u + (uint32_t)sb * kHBStage, b_small = b_big + kHTile;
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
     };
     auto gemm2 = [&](int it) {
       const int buf = it & 1;
-      mbar_wait(&sm.d2_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 42);  // epilogue-2 of item it-2 has drained D2[buf]
+      mbar_wait(&sm.d2_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 42, 20);  // epilogue-2 of item it-2 has drained D2[buf]
       tc_fence_after();
       const uint32_t d2 = tmem_u + (uint32_t)(2 * kHHidden + buf * kHHidden);
       block(g2(it, 0), 4, d2, true, nullptr);
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
     // ==================================================================================================== weight tiles
     auto load = [&](uint32_t g, const uint8_t* tile) {
       const int sb = (int)(g % SB);
-      mbar_wait(&sm.b_empty[sb], (uint32_t)(((g / SB) & 1) ^ 1), 60);
+      mbar_wait(&sm.b_empty[sb], (uint32_t)(((g / SB) & 1) ^ 1), 60, 128);
       if (elect_one()) {
         mbar_arrive_expect_tx(&sm.b_full[sb], kHBStage);
         bulk_g2s(ring_b + (size_t)sb * kHBStage, tile, kHBStage, &sm.b_full[sb]);

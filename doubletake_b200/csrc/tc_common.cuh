@@ -36,30 +36,37 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug traps (CUDA error after ~2 s) instead of hanging the GPU box.
-// try_wait carries a suspend-time hint: the hardware parks the thread until the phase flips or the hint (in ns) expires, so
-// a waiting warp issues a handful of instructions per wait instead of polling -- in round 1's profiles the polling loops of
-// waiting warps were ~30 % of all issued instructions and competed with the warps doing the work.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+// `sleep_ns` > 0 backs off between polls (exponentially, capped at 8 x sleep_ns).  A polling warp issues ~8 instructions
+// and one shared-memory access every ~30 clk: measured in round 2, the waiting roles of the persistent kernels (epilogue,
+// loaders, the idle MMA warp) took ~30 % of all issue slots away from the producer warps.  Roles whose wake-up latency is
+// not on the critical path therefore sleep; the default (0) is the tight loop.
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0, uint32_t sleep_ns = 0) {
   const uint32_t addr = smem_u32(bar);
-  long long t0 = 0;
-  for (uint32_t spin = 0;; ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(0x989680u)
-        : "memory");
-    if (done) return;
-    if ((spin & 0x3F) == 0x3F) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000LL) {
-        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)
-          printf("mbar timeout: warp %d tag %d bar@%u parity %u\n", (int)(threadIdx.x >> 5), tag, addr, parity);
-        if (now - t0 > 2400000000LL) __trap();
-      }
+  if (mbar_try(addr, parity)) return;
+  const long long t0 = clock64();
+  uint32_t ns = sleep_ns;
+  for (;;) {
+    if (ns) {
+      __nanosleep(ns);
+      if (ns < 8 * sleep_ns) ns <<= 1;
+    }
+    if (mbar_try(addr, parity)) return;
+    const long long waited = clock64() - t0;
+    if (waited > 2000000000LL) {
+      if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)
+        printf("mbar timeout: warp %d tag %d bar@%u parity %u\n", (int)(threadIdx.x >> 5), tag, addr, parity);
+      if (waited > 2400000000LL) __trap();
     }
   }
 }

@@ -26,13 +26,15 @@ from . import _lib as L
 # plan builder
 # ----------------------------------------------------------------------------------------------------------------
 class Feature:
-    """A channels-last activation buffer (B,H,W,C) inside a plan."""
+    """A channels-last activation buffer (B,H,W,C) inside a plan.  ``fmt``: "f32" = plain fp32 NHWC; "split16" = the
+    tensor-core layout of math "tch", (B,H,W,2,C) fp16 big | small planes in the same bytes (include/doubletake_b200.h)."""
 
-    __slots__ = ("t", "b", "h", "w", "c")
+    __slots__ = ("t", "b", "h", "w", "c", "fmt")
 
-    def __init__(self, t):
+    def __init__(self, t, fmt="f32"):
         self.t = t
         self.b, self.h, self.w, self.c = t.shape
+        self.fmt = fmt
 
 
 class ConvPlan:
@@ -55,15 +57,31 @@ class ConvPlan:
         self.max_lanes = int(os.environ.get("DTB200_CONV_LANES", "8"))
         self.workspace_slots = int(os.environ.get("DTB200_CONV_WS_SLOTS", "6"))
 
-    def new(self, b, h, w, c):
+    def new(self, b, h, w, c, fmt=None):
+        """A fresh buffer.  In a "tch" plan every map with a multiple of 8 channels is split16 (same bytes as fp32)."""
+        if fmt is None:
+            fmt = "split16" if (self.math == L.MATH_TCH and c % 8 == 0) else "f32"
         t = torch.empty((b, h, w, c), dtype=torch.float32, device=self.device)
         self.keep.append(t)
-        return Feature(t)
+        return Feature(t, fmt)
 
     def input(self, name, b, c, h, w):
+        if self.math == L.MATH_TCH and c % 8 != 0:
+            raise ValueError(f"math='tch' needs input maps with a multiple of 8 channels, {name} has {c}")
         f = self.new(b, h, w, c)
         self.inputs[name] = f
         return f
+
+    def set_feature(self, f, x_nchw):
+        """Fill a plan buffer from an NCHW fp32 CUDA tensor in the buffer's own layout."""
+        if tuple(x_nchw.shape) != (f.b, f.c, f.h, f.w):
+            raise ValueError(f"expected {(f.b, f.c, f.h, f.w)}, got {tuple(x_nchw.shape)}")
+        if not x_nchw.is_cuda:
+            raise RuntimeError("doubletake_b200 networks run on CUDA only (no CPU fallback)")
+        if f.fmt == "split16":
+            L.nchw_to_split16(x_nchw, f.t)
+        else:
+            L.nchw_to_nhwc(x_nchw, out=f.t)
 
     def _pack(self, weight, src_channels):
         """Device copy of an OIHW weight in the layout the math mode consumes, for this concat split of its inputs."""
@@ -99,7 +117,7 @@ class ConvPlan:
 
     def conv(self, srcs, conv: nn.Conv2d, act=L.ACT_NONE, slope=0.0, residual=None):
         """srcs: list of (Feature, resample).  Returns the output Feature."""
-        if self.math == L.MATH_TC3X and conv.out_channels % 64 == 0:
+        if self.math in (L.MATH_TC3X, L.MATH_TCH) and conv.out_channels % 64 == 0:
             # tensor-core path: interpolate once, not once per tap per consumer
             srcs = [(self.upsampled(f, r), L.RESAMPLE_NONE) if r != L.RESAMPLE_NONE else (f, r) for f, r in srcs]
         k = conv.kernel_size[0]
@@ -131,10 +149,15 @@ class ConvPlan:
             self.keep.append(bias)
             self._tracked.append((conv.bias, conv.bias._version))
             op.bias = L.ptr(bias)
-        out = self.new(f0.b, out_h, out_w, conv.out_channels)
+        if self.math == L.MATH_TCH:
+            if any(f.fmt != "split16" for f, _ in srcs):
+                raise ValueError("math='tch': every conv source must be a split16 map (a multiple of 8 channels)")
+            out = self.new(f0.b, out_h, out_w, conv.out_channels, "split16" if conv.out_channels % 64 == 0 else "f32")
+        else:
+            out = self.new(f0.b, out_h, out_w, conv.out_channels)
         if residual is not None:
-            if (residual.b, residual.h, residual.w, residual.c) != (out.b, out.h, out.w, out.c):
-                raise ValueError("residual shape mismatch")
+            if (residual.b, residual.h, residual.w, residual.c) != (out.b, out.h, out.w, out.c) or residual.fmt != out.fmt:
+                raise ValueError("residual shape / layout mismatch")
             op.residual = L.ptr(residual.t)
         op.act, op.act_slope = act, slope
         op.dst = L.ptr(out.t)
@@ -200,9 +223,7 @@ class ConvPlan:
             f = self.inputs[name]
             if tuple(x.shape) != (f.b, f.c, f.h, f.w):
                 raise ValueError(f"plan input {name}: expected {(f.b, f.c, f.h, f.w)}, got {tuple(x.shape)}")
-            if not x.is_cuda:
-                raise RuntimeError("doubletake_b200 networks run on CUDA only (no CPU fallback)")
-            L.nchw_to_nhwc(x, out=f.t)
+            self.set_feature(f, x)
 
     def output_nchw(self, f):
         """A plan buffer as a fresh NCHW fp32 tensor (what the reference-facing ``forward`` methods return)."""
@@ -221,7 +242,9 @@ class ConvPlan:
 
 
 def _nchw_out(f: Feature):
-    """Plan output -> fresh NCHW tensor (1-channel maps are a pure reshape)."""
+    """Plan output -> fresh NCHW fp32 tensor (1-channel fp32 maps are a pure reshape)."""
+    if f.fmt == "split16":
+        return L.split16_to_nchw(f.t, f.b, f.c, f.h, f.w)
     if f.c == 1:
         return f.t.reshape(f.b, 1, f.h, f.w).clone()
     return L.nhwc_to_nchw(f.t)

@@ -46,6 +46,11 @@ uint64_t dtb200_launch_count(void);
  * ---------------------------------------------------------------------------------------------------------- */
 int dtb200_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, dtb200_stream_t stream);
 int dtb200_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, dtb200_stream_t stream);
+/* math = TCH keeps activations in the "split16" layout: (N, H, W, 2, C) fp16 -- per pixel C values big = fp16(x) followed by
+ * C values small = fp16((x - big) * 2048); 4C bytes per pixel like fp32, 22 significant bits, clamped to the fp16 range.
+ * c must be a multiple of 8.  A split16 tensor occupies exactly the bytes of the (N, H, W, C) fp32 tensor. */
+int dtb200_nchw_to_split16(const float* src, void* dst, int n, int c, int h, int w, dtb200_stream_t stream);
+int dtb200_split16_to_nchw(const void* src, float* dst, int n, int c, int h, int w, dtb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Plane-sweep cost volumes.
@@ -133,6 +138,9 @@ int dtb200_cost_volume(const dtb200_cost_volume_params* p, dtb200_stream_t strea
 
 #define DTB200_CONV_MAX_SRC 3
 
+/* math = TCH: src[] and residual are split16 tensors (see dtb200_nchw_to_split16), dst is written as split16 when out_c is a
+ * multiple of 64 and as plain fp32 NHWC otherwise (the 1-channel heads); x2-resampled sources must be materialised first
+ * with a ksize = 0 descriptor (split16 -> split16), as for TC3X. */
 typedef struct {
   int32_t math;                 /* DTB200_MATH_* */
   int32_t batch;

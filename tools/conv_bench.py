@@ -61,7 +61,7 @@ def run(args, dev):
         for i, (c, r) in enumerate(srcs):
             h, w = (H // 2, W // 2) if r else (H, W)
             f = plan.new(1, h, w, c)
-            f.t.normal_()
+            plan.set_feature(f, torch.randn(1, c, h, w, device=dev))
             feats.append((f, r))
         conv = nn.Conv2d(sum(c for c, _ in srcs), oc, k, stride=stride, padding=k // 2)
         plan.conv(feats, conv, L.ACT_LEAKY, 0.2)
