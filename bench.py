@@ -32,10 +32,19 @@ from doubletake_b200 import synthetic as syn  # noqa: E402
 
 METRIC = "depth frames/sec at 640x480x64planes x7views"
 UNIT = "frames/s"
-WORKLOAD = "cfg2"
 L2_FLUSH_BYTES = 256 << 20
-WORKLOAD_DESC = ("cfg2: DoubleTake 640x480 image, 120x160x16 matching feats, 64 planes, 7 src views, "
-                 "rendered-depth hint on, batch 1 per GPU, CVEncoder+DepthDecoderPP (effnetv2-s priors)")
+# BASELINE.json configs: [1] = cfg2 is the headline metric's configuration (the default); cfg3 / cfg5 are the other two
+# single-GPU throughput configurations, benchmarked with --workload and committed under profiles/
+WORKLOADS = {
+    "cfg2": (METRIC, "cfg2: DoubleTake 640x480 image, 120x160x16 matching feats, 64 planes, 7 src views, "
+                     "rendered-depth hint on, batch 1 per GPU, CVEncoder+DepthDecoderPP (effnetv2-s priors)"),
+    "cfg3": ("depth frames/sec at 512x384x48planes x5views, batch 8 (DoubleTake-small)",
+             "cfg3: DoubleTake-small 512x384 image, 96x128x16 matching feats, 48 planes, 5 src views, hint on, batch 8 per GPU, "
+             "CVEncoder+SkipDecoderRegression (resnet18d priors)"),
+    "cfg5": ("depth frames/sec at 1024x768x96planes x9views, batch 4 (stress)",
+             "cfg5: synthetic stress 1024x768 image, 192x256x16 matching feats, 96 planes, 9 src views, hint on, batch 4 per GPU, "
+             "CVEncoder+DepthDecoderPP (effnetv2-s priors)"),
+}
 
 
 def measured_peaks():
@@ -92,6 +101,13 @@ def tree_bytes(d):
         for x in (v if isinstance(v, (list, tuple)) else [v]):
             n += x.numel() * x.element_size()
     return n
+
+
+def model_options(cfg):
+    import doubletake_b200 as dt
+    return dt.HotPathOptions(image_encoder_name="efficientnet" if cfg.prior_ch[0] == 24 else "resnet18d",
+                             depth_decoder_name=cfg.decoder, matching_num_depth_bins=cfg.planes,
+                             model_num_views=cfg.num_src + 1, image_height=cfg.image_h, image_width=cfg.image_w)
 
 
 def model_weights(model, seed=2024):
@@ -163,6 +179,13 @@ class ClockSampler:
             os.unlink(self.path)
         except Exception:
             pass
+        self.rows = rows
+        return self.window_stats(windows)
+
+    def window_stats(self, windows):
+        """Median SM clock / throttle reasons over the samples inside the given (t0, t1) wall-clock windows."""
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        rows = getattr(self, "rows", [])
         inside = [r for r in rows if r[0] is not None and any(t0 - 0.05 <= r[0] <= t1 + 0.05 for t0, t1 in windows)]
         out["window"] = "timed regions" if inside else "whole run (no sample fell inside the timed regions)"
         use = inside or rows
@@ -196,9 +219,9 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.set_grad_enabled(False)
 
-    cfg = syn.CONFIGS[WORKLOAD]
-    opts = dt.HotPathOptions(matching_num_depth_bins=cfg.planes, model_num_views=cfg.num_src + 1,
-                             image_height=cfg.image_h, image_width=cfg.image_w)
+    cfg = syn.CONFIGS[args.workload]
+    metric, workload_desc = WORKLOADS[args.workload]
+    opts = model_options(cfg)
     volume_math = args.volume_math or ("exact" if args.math == "exact" else "tch")
     model = dt.DepthModelCVHint(opts, math=args.math, volume_math=volume_math)
     model.load_state_dict(model_weights(model), strict=False)
@@ -286,27 +309,52 @@ def run_b200(args):
         step_e2e(i)
     barrier()
     e2e_s = reduce_max(time.perf_counter() - t0)
-    clocks = sampler.stop([(w_timed0, w_timed1), (w_e2e0, time.time())]) if rank == 0 else None
+    w_e2e1 = time.time()
+
+    # ---- sustained figure: the same resident step back to back for >= --sustain seconds (no L2 flush: 4 rotating input
+    # sets), one event pair around the whole loop, with its own clock record (power-capped clocks differ from the burst)
+    sustained = None
+    if args.sustain > 0:
+        n_sus = max(args.steps, int(args.sustain / max(dev_ms / args.steps / 1e3, 1e-6)) + 1)
+        barrier()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w_sus0 = time.time()
+        s_ev.record()
+        for i in range(n_sus):
+            step_resident(i)
+        e_ev.record()
+        barrier()
+        w_sus1 = time.time()
+        sus_ms = reduce_max(s_ev.elapsed_time(e_ev))
+        sustained = {"value": round(frames_per_step * n_sus / (sus_ms / 1e3), 3), "unit": UNIT, "steps": n_sus,
+                     "seconds": round(sus_ms / 1e3, 3), "ms_per_step": round(sus_ms / n_sus, 4)}
+    if rank == 0:
+        clocks = sampler.stop([(w_timed0, w_timed1), (w_e2e0, w_e2e1)])
+        if sustained is not None:
+            sustained["clocks"] = sampler.window_stats([(w_sus0, w_sus1)])
+    else:
+        clocks = None
 
     # ---- per-kernel timing for the roofline (rank 0, N=1 semantics): cost-volume kernel and the conv plan, alone
     roof = None
     cpu_base = None
     if rank == 0:
         roof = kernel_rooflines(model, dev_sets, cfg, flush, L)
+        ref_gpu = reference_on_gpu(cfg, model, dev) if (world == 1 and not args.no_reference_gpu) else None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_base = cpu_baseline(cfg, budget_s=args.cpu_budget)
+            cpu_base = cpu_baseline(args.workload, budget_s=args.cpu_budget)
 
     if rank == 0:
         ms_per_step = dev_ms / args.steps
         value = frames_per_step / (ms_per_step / 1e3)
         line = {
-            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"exact": "f32", "tc3x": "f32 via 3xTF32 (tf32 big/small split, fp32 accumulate)",
                       "tch": "f32 via 2-term fp16 split (big + small/2048, three kind::f16 MMAs per product, fp32 accumulate)"}[args.math],
             "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC, "math": args.math, "volume_math": volume_math, "frames_per_step": frames_per_step,
+            "config": {"workload": workload_desc, "math": args.math, "volume_math": volume_math, "frames_per_step": frames_per_step,
                        "l2": "256 MiB L2 flush between timed steps (outside the per-step event pairs); 4 rotating input sets",
                        "weights": "random-init (seeded), reference architecture",
                        "wall_ms_per_step_incl_flush": round(1e3 * t_wall / args.steps, 4)},
@@ -314,6 +362,8 @@ def run_b200(args):
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": host_out.numel() * 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "sustained": sustained,
+            "reference_gpu": ref_gpu,
             "roofline": roof["dominant"] if roof else None,
             "roofline_kernels": roof["all"] if roof else None,
             "cpu_baseline": cpu_base,
@@ -405,41 +455,74 @@ def kernel_rooflines(model, dev_sets, cfg, flush, L, reps=5):
 
 
 # --------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's path on the host cores
+# reference arms: the oracle port of the reference's path (a) in eager fp32 torch on the same B200, (b) on the host cores
 # --------------------------------------------------------------------------------------------------------------
-def cpu_sample_config(width_div):
-    c = syn.CONFIGS[WORKLOAD]
-    return syn.WorkloadConfig(f"cfg2_w{width_div}", c.batch, c.num_src, c.image_h, c.image_w // width_div, c.planes,
-                              hint=True, prior_ch=c.prior_ch, decoder=c.decoder, seed=c.seed)
-
-
-def cpu_step_fn(cfg_s):
-    """One pass of the reference algorithm (oracle port) over a 1/width_div-width crop of the cfg-2 frame: identical
-    per-pixel work (64 planes, 7 views, full conv stack), fewer pixels."""
+def oracle_step_fn(cfg_s, device="cpu"):
+    """One pass of the reference algorithm (oracle port: the reference's torch ops in the reference's order) over the
+    workload ``cfg_s`` with every tensor on ``device``."""
     from oracle import oracle_torch as orc
     import doubletake_b200 as dt
 
     inp = syn.cost_volume_inputs(cfg_s)
-    priors = syn.prior_features(cfg_s)
-    opts = dt.HotPathOptions(matching_num_depth_bins=cfg_s.planes, model_num_views=cfg_s.num_src + 1,
-                             image_height=cfg_s.image_h, image_width=cfg_s.image_w)
-    shapes = {k: tuple(v.shape) for k, v in dt.DepthModelCVHint(opts).named_parameters()}
-    w = syn.seeded_state_dict(shapes, 2024, 1.3)
+    priors = [p.to(device) for p in syn.prior_features(cfg_s)]
+    shapes = {k: tuple(v.shape) for k, v in dt.DepthModelCVHint(model_options(cfg_s)).named_parameters()}
+    w = {k: v.to(device) for k, v in syn.seeded_state_dict(shapes, 2024, 1.3).items()}
     eye = torch.eye(4).expand(cfg_s.batch, 4, 4).contiguous()
     cur = {"cam_T_world_b44": eye, "world_T_cam_b44": eye, "invK_s1_b44": inp["cur_invK"], **inp["cv_depth_hint_dict"]}
     src = {"cam_T_world_b44": inp["src_extrinsics"], "world_T_cam_b44": inp["src_poses"], "K_s1_b44": inp["src_Ks"]}
+    cur = {k: v.to(device) for k, v in cur.items()}
+    src = {k: v.to(device) for k, v in src.items()}
+    mc, ms = inp["cur_feats"].to(device), inp["src_feats"].to(device)
 
     def step():
-        return orc.depth_model_forward(inp["cur_feats"], inp["src_feats"], priors, cur, src, w, cfg_s.planes, hint=True)
+        return orc.depth_model_forward(mc, ms, priors, cur, src, w, cfg_s.planes, hint=True, decoder=cfg_s.decoder)
 
     return step
 
 
-def pick_cpu_sample(total_steps, budget_s):
+def reference_on_gpu(cfg, model, dev, reps=3):
+    """BASELINE.md 3.3 / SURVEY 8d: the reference's own algorithm in eager fp32 PyTorch on the SAME B200 -- the bar a GPU
+    user of the reference has today (the per-plane Python loop of the slow manager, cuDNN / cuBLAS kernels, TF32 off).
+    Timed like test_no_hint.py:161-175 (synchronise, wall clock around forward), 1 warm-up + `reps` passes, median."""
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        step = oracle_step_fn(cfg, dev)
+        step()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            step()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return {"value": round(cfg.batch / med, 3), "unit": UNIT, "ms_per_step": round(med * 1e3, 2), "reps": reps,
+            "kind": "port: oracle/oracle_torch.py (the reference's torch ops in the reference's order) in eager fp32 on this GPU, "
+                    "encoders' outputs supplied like in the B200 arm"}
+
+
+def cpu_sample_config(workload, width_div):
+    c = syn.CONFIGS[workload]
+    return syn.WorkloadConfig(f"{workload}_w{width_div}", c.batch, c.num_src, c.image_h, c.image_w // width_div, c.planes,
+                              hint=True, prior_ch=c.prior_ch, decoder=c.decoder, seed=c.seed)
+
+
+def cpu_step_fn(cfg_s):
+    """One pass of the reference algorithm (oracle port) over a 1/width_div-width crop of the frame: identical per-pixel
+    work (all planes, all views, full conv stack), fewer pixels."""
+    return oracle_step_fn(cfg_s, "cpu")
+
+
+def pick_cpu_sample(workload, total_steps, budget_s):
     """Probe a 1/10-width crop, then choose the largest crop (width stays a multiple of 32) whose total run fits
     the budget."""
     ncpu = os.cpu_count() or 1
-    probe = cpu_step_fn(cpu_sample_config(10))
+    probe = cpu_step_fn(cpu_sample_config(workload, 16 if workload == "cfg5" else 10))
     # "all the host threads it can use": torch's CPU ops on this path stop scaling (and regress) well below the
     # core count of the GPU hosts, so probe a few thread counts and keep the fastest
     best = None
@@ -452,24 +535,35 @@ def pick_cpu_sample(total_steps, budget_s):
         if best is None or t < best[0]:
             best = (t, n)
     t10, cores = best
+    probe_div = 16 if workload == "cfg5" else 10
     torch.set_num_threads(cores)
-    for div in (1, 2, 4, 10, 20):
-        if t10 * (10 / div) * total_steps <= budget_s or div == 20:
+    for div in (1, 2, 4, 8, 16, 32):
+        if syn.CONFIGS[workload].image_w % (32 * div) and div != 1:
+            continue
+        if t10 * (probe_div / div) * total_steps <= budget_s or div == 32:
             return div, cores
+    return 32, cores
 
 
-def cpu_baseline(cfg, budget_s=25.0):
+def cpu_baseline(workload, budget_s=25.0, reps=3):
+    """1 warm-up + >= 3 timed passes, median (and min) reported."""
     torch.set_grad_enabled(False)
-    div, cores = pick_cpu_sample(2, budget_s)
-    step = cpu_step_fn(cpu_sample_config(div))
+    c = syn.CONFIGS[workload]
+    div, cores = pick_cpu_sample(workload, reps + 1, budget_s)
+    step = cpu_step_fn(cpu_sample_config(workload, div))
     step()
-    t0 = time.perf_counter()
-    step()
-    dt_s = time.perf_counter() - t0
-    return {"value": round((1.0 / div) / dt_s, 5), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle (torch CPU restatement of the reference path), 1 warm-up + 1 timed pass over a 1/{div}-width "
-                      f"crop of the cfg-2 frame (480x{640 // div} image, 64 planes, 7 views, hint, full conv stack) = "
-                      f"{1.0 / div:.3f} frame in {dt_s:.2f} s"}
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return {"value": round((c.batch / div) / med, 5), "unit": UNIT, "cores": cores, "kind": "port",
+            "min_s": round(ts[0], 3), "median_s": round(med, 3), "reps": reps,
+            "sample": f"oracle (torch CPU restatement of the reference path), 1 warm-up + {reps} timed passes (median) over a "
+                      f"1/{div}-width crop of the {workload} batch ({c.image_h}x{c.image_w // div} image, {c.planes} planes, "
+                      f"{c.num_src} views, hint, full conv stack, batch {c.batch}) = {c.batch / div:.3f} frame(s) in {med:.2f} s"}
 
 
 def run_reference(args):
@@ -479,22 +573,25 @@ def run_reference(args):
         return
     torch.set_grad_enabled(False)
     warm = max(args.warmup, 1)
-    div, cores = pick_cpu_sample(args.steps + warm, args.ref_budget)
-    step = cpu_step_fn(cpu_sample_config(div))
+    c = syn.CONFIGS[args.workload]
+    metric, workload_desc = WORKLOADS[args.workload]
+    div, cores = pick_cpu_sample(args.workload, args.steps + warm, args.ref_budget)
+    step = cpu_step_fn(cpu_sample_config(args.workload, div))
     for _ in range(warm):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt_s = time.perf_counter() - t0
-    value = args.steps * (1.0 / div) / dt_s
-    sample = (f"each step = oracle port of the reference path over a 1/{div}-width crop of the cfg-2 frame "
-              f"(480x{640 // div} image, 64 planes, 7 views, hint, full conv stack) = {1.0 / div:.3f} frame")
+    value = args.steps * (c.batch / div) / dt_s
+    sample = (f"each step = oracle port of the reference path over a 1/{div}-width crop of the {args.workload} batch "
+              f"({c.image_h}x{c.image_w // div} image, {c.planes} planes, {c.num_src} views, hint, full conv stack, batch {c.batch}) "
+              f"= {c.batch / div:.3f} frame(s)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": world,
+        "impl": "reference", "metric": metric, "value": round(value, 5), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": round(1e3 * dt_s / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC, "math": "f32 (reference algorithm, torch CPU ops, host threads)",
+        "config": {"workload": workload_desc, "math": "f32 (reference algorithm, torch CPU ops, host threads)",
                    "sample": sample},
         "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -513,6 +610,10 @@ def main():
                          "default); tc3x: 3xTF32 split; exact: fp32 CUDA cores")
     ap.add_argument("--volume-math", default=None, choices=["exact", "tc3x", "tch"],
                     help="cost-volume MLP arithmetic; default: tch (kind::f16, 2-term fp16 split) unless --math exact")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
+                    help="cfg2 = the headline metric's configuration (default); cfg3 / cfg5 = BASELINE.json configs[2] / [4]")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back steps for the `sustained` figure (0 = off)")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the eager-PyTorch-on-this-GPU reference timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--ref-budget", type=float, default=150.0)

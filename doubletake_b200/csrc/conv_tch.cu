@@ -31,9 +31,9 @@ using namespace tc;
 constexpr int kCM = 128;              // pixels per tile (UMMA M)
 constexpr int kCK = 64;               // fp16 channels per K block = one 128-byte swizzled row
 constexpr int kCTile = kCM * 128;     // 16 KB: [128 pixels][64 fp16]
-constexpr int kCEpiWarps = 4;         // warps 0-3: TMEM lane quadrant == warp index
-constexpr int kCMmaWarp = 4, kCLoadA = 5, kCLoadB = 6;
-constexpr int kCThreads = 7 * 32;
+constexpr int kCEpiWarps = 8;         // warps 0-7: TMEM lane quadrant = warp & 3, the two warps of a quadrant split the columns
+constexpr int kCMmaWarp = 8, kCLoadA = 9, kCLoadB = 10;
+constexpr int kCThreads = 11 * 32;
 
 // K layout shared by the weight packer and the kernels: tap-major; inside a tap the sources in order, each cut into
 // 64-channel chunks (the last chunk of a source may overhang: TMA zero-fills, the packer writes zero weights).
@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_tch_kernel(const dtb200_con
 
   if (warp < kCEpiWarps) {
     // ============================================================ epilogue
-    const int row = warp * 32 + lane;
+    const int qd = warp & 3, chalf = warp >> 2;
+    const int row = qd * 32 + lane;
     const int ty = row / wk.tw, tx = row - ty * wk.tw;
     int use = 0;
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
@@ -203,9 +204,9 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_tch_kernel(const dtb200_con
       const int n_base = n_tile * BN;
       mbar_wait(&acc_full[buf], (use >> 1) & 1, 1, 128);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(buf * Cfg::kAccCols) + ((uint32_t)(warp * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * Cfg::kAccCols) + ((uint32_t)(qd * 32) << 16);
 #pragma unroll 1
-      for (int cc = 0; cc < BN; cc += 32) {
+      for (int cc = chalf * (BN / 2); cc < (chalf + 1) * (BN / 2); cc += 32) {
         float v[32], c[32];
         tmem_ld32(taddr + (uint32_t)cc, v);
         tmem_ld32(taddr + (uint32_t)(BN + cc), c);
@@ -386,7 +387,8 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_tch_halo_kernel(const dtb20
 
   if (warp < kCEpiWarps) {
     // ============================================================ epilogue
-    const int row = warp * 32 + lane;
+    const int qd = warp & 3, chalf = warp >> 2;
+    const int row = qd * 32 + lane;
     const int ty = row / kHTW, tx = row - ty * kHTW;
     int use = 0;
     for (long long item = blockIdx.x; item < wk.total; item += gridDim.x, ++use) {
@@ -399,9 +401,9 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_tch_halo_kernel(const dtb20
       const int n_base = n_tile * BN;
       mbar_wait(&acc_full[buf], (use >> 1) & 1, 1, 128);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(buf * kAccCols) + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-      for (int cc = 0; cc < BN; cc += 32) {
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * kAccCols) + ((uint32_t)(qd * 32) << 16);
+      {
+        const int cc = chalf * 32;   // BN = 64: one 32-column chunk per warp
         float v[32], c[32];
         tmem_ld32(taddr + (uint32_t)cc, v);
         tmem_ld32(taddr + (uint32_t)(BN + cc), c);

@@ -61,7 +61,10 @@ struct CvhSmall {
   float hw[224];                 // hint MLP: hw1 (36) hb1 (12) hw2 (144) hb2 (12) hw3 (12) hb3 (1)
   float partial[2][kHRows];
   float score[kHRows];
-  uint64_t a_full[kHAStages], a_empty[kHAStages], b_full[kHBStages], b_empty[kHBStages];
+  // a_empty is kept PER WRITER GROUP (0 = producers, 1 / 2 = epilogue column halves): the A ring is shared by three writer
+  // groups and a parity wait is only sound if the waiter has observed every earlier phase of the barrier it waits on, so
+  // the MMA warp routes the "stage consumed" signal to the barrier of the group that writes the stage's NEXT use
+  uint64_t a_full[kHAStages], a_empty[3][kHAStages], b_full[kHBStages], b_empty[kHBStages];
   uint64_t d1_full[2], d2_full[2], d2_empty[2];
   uint32_t tmem_slot;
 };
@@ -134,7 +137,10 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
   const int n = it_end - it_begin;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(&sm.a_full[s], kProdWarps), mbar_init(&sm.a_empty[s], 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&sm.a_full[s], kProdWarps);
+      for (int w = 0; w < 3; ++w) mbar_init(&sm.a_empty[w][s], 1);
+    }
     for (int s = 0; s < SB; ++s) mbar_init(&sm.b_full[s], 1), mbar_init(&sm.b_empty[s], 1);
     for (int s = 0; s < 2; ++s) mbar_init(&sm.d1_full[s], 1), mbar_init(&sm.d2_full[s], 1), mbar_init(&sm.d2_empty[s], kHEpiWarps);
     fence_mbar_init();
@@ -165,6 +171,24 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
   auto g2 = [&](int it, int j) -> uint32_t {
     return it < n - 1 ? (uint32_t)(nkb1 + it * (nkb1 + 2) + nkb1 + j) : (uint32_t)(nkb1 + (n - 1) * (nkb1 + 2) + j);
   };
+  // which group writes K block g of the sequence: 0 = producers (GEMM1 operands), 1 + j = epilogue half j (h1 block j), -1 = none
+  auto writer_of = [&](uint32_t g) -> int {
+    const uint32_t tail = (uint32_t)(nkb1 + (n - 1) * (nkb1 + 2));   // first block of the final GEMM2
+    if (g >= tail + 2) return -1;
+    if (g >= tail) return 1 + (int)(g - tail);
+    if (g < (uint32_t)nkb1) return 0;
+    const uint32_t r = (g - (uint32_t)nkb1) % (uint32_t)(nkb1 + 2);
+    return r < (uint32_t)nkb1 ? 0 : 1 + (int)(r - (uint32_t)nkb1);
+  };
+  // a writer's wait for "the previous use of this stage has been consumed": every group sees exactly the completions of
+  // its own uses, in order, so one parity bit per stage (flipped after every wait) is exact; the first S blocks of the
+  // sequence have no predecessor
+  auto wait_stage_free = [&](int group, uint32_t g, uint32_t& pbits, int tag, uint32_t sleep_ns) {
+    if (g < (uint32_t)S) return;
+    const int st = (int)(g % S);
+    mbar_wait(&sm.a_empty[group][st], (pbits >> st) & 1u, tag, sleep_ns);
+    pbits ^= 1u << st;
+  };
   auto decode = [&](int it, int& b, int& pix0, int& d0) {
     const uint32_t item = (uint32_t)(it_begin + it);
     const uint32_t per_b = (uint32_t)(wk.pix_groups * wk.plane_chunks);
@@ -186,6 +210,7 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
     const float b3 = __ldg(p.b3);
     const uint32_t lane_bits = (uint32_t)(qd * 32) << 16;
     const uint32_t ring_u = smem_u32(ring_a);
+    uint32_t ebits = 0;   // per-stage wait parities of this epilogue half
 
     auto epi1 = [&](int it) {
       const int buf = it & 1;
@@ -193,7 +218,7 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
       tc_fence_after();
       const uint32_t g = g2(it, half);
       const int st = (int)(g % S);
-      mbar_wait(&sm.a_empty[st], (uint32_t)(((g / S) & 1) ^ 1), 21, 32);
+      wait_stage_free(1 + half, g, ebits, 21, 32);
       const uint32_t a_big = ring_u + (uint32_t)st * kHAStage;
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
@@ -309,6 +334,7 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
     const int npass = (K + 4) / 4;   // ceil((K + 1) slots / 4)
     const uint32_t ring_u = smem_u32(ring_a);
     int cur_b = -1;
+    uint32_t pbits = 0;   // per-stage wait parities of the producer group
 
     for (int it = 0; it < n; ++it) {
       int b, pix0, d0;
@@ -360,8 +386,8 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
         const bool has_b = kb0 + 1 < nkb1;
         const uint32_t gA = g1(it, kb0), gB = gA + 1;
         const int stA = (int)(gA % S), stB = (int)(gB % S);
-        mbar_wait(&sm.a_empty[stA], (uint32_t)(((gA / S) & 1) ^ 1), 10, 64);
-        if (has_b) mbar_wait(&sm.a_empty[stB], (uint32_t)(((gB / S) & 1) ^ 1), 11, 64);
+        wait_stage_free(0, gA, pbits, 10, 64);
+        if (has_b) wait_stage_free(0, gB, pbits, 11, 64);
         const uint32_t baseA = ring_u + (uint32_t)stA * kHAStage, baseB = ring_u + (uint32_t)stB * kHAStage;
         const int my_slot = 4 * pass + q;   // the slot whose per-(row, view) scalar work this lane does
 #pragma unroll
@@ -483,7 +509,8 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
           umma_f16(tmem_d, da_b, db_s, idesc, true);
           umma_f16(tmem_d, da_b, db_b, idesc, true);
         }
-        umma_commit(&sm.a_empty[st]);
+        const int next_writer = writer_of(g + S);
+        if (next_writer >= 0) umma_commit(&sm.a_empty[next_writer][st]);
         umma_commit(&sm.b_empty[sb]);
         if (done_bar) umma_commit(done_bar);
       }

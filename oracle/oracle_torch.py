@@ -68,7 +68,7 @@ def warp_sources(src_feats, pix_bk2N, H, W):
     """modules/mesh_hint_volume.py:238-249: uv = 2*pix*[1/W,1/H] - 1, bilinear grid_sample, zeros padding,
     align_corners=False.  -> (B,K,C,H,W)."""
     B, K, C = src_feats.shape[:3]
-    uv_scale = torch.tensor([1 / W, 1 / H], dtype=torch.float32).view(1, 1, 1, 2)
+    uv_scale = torch.tensor([1 / W, 1 / H], dtype=torch.float32, device=src_feats.device).view(1, 1, 1, 2)
     grid = pix_bk2N.reshape(B * K, 2, H, W).permute(0, 2, 3, 1)
     grid = 2 * grid * uv_scale - 1
     warped = F.grid_sample(
@@ -100,8 +100,10 @@ def cost_volume_dot(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur
     the current features, multiply by the depth-validity mask, sum over views.
     Returns dict(volume (B,D,H,W), lowest_cost (B,H,W), index (B,H,W) int64, planes (D,))."""
     B, K, C, H, W = src_feats.shape
-    planes = depth_planes(min_depth, max_depth, num_planes)
-    pix = pixel_grid(H, W)
+    # evaluated on the CPU (bit-identical planes / grid), then moved: the oracle also runs on CUDA tensors (bench.py times
+    # it there as the "reference on the same B200" arm)
+    planes = depth_planes(min_depth, max_depth, num_planes).to(cur_feats.device)
+    pix = pixel_grid(H, W).to(cur_feats.device)
     vols = []
     for d in planes:
         X = backproject(d, cur_invK, pix)
@@ -136,8 +138,10 @@ def feature_volume(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_
     (mesh_hint_volume.py:273-287).
     """
     B, K, C, H, W = src_feats.shape
-    planes = depth_planes(min_depth, max_depth, num_planes)
-    pix = pixel_grid(H, W)
+    # evaluated on the CPU (bit-identical planes / grid), then moved: the oracle also runs on CUDA tensors (bench.py times
+    # it there as the "reference on the same B200" arm)
+    planes = depth_planes(min_depth, max_depth, num_planes).to(cur_feats.device)
+    pix = pixel_grid(H, W).to(cur_feats.device)
     comb, r_m, t_m = pose_measures(src_poses)
 
     def bc(x):  # (B,K) -> (B,K,H,W)

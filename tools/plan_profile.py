@@ -58,7 +58,8 @@ def main():
     cfg = syn.CONFIGS["cfg2"]
     opts = dt.HotPathOptions(matching_num_depth_bins=cfg.planes, model_num_views=cfg.num_src + 1,
                              image_height=cfg.image_h, image_width=cfg.image_w)
-    model = dt.DepthModelCVHint(opts, math="tc3x", volume_math="tc3x")
+    math = os.environ.get("DTB200_PLAN_MATH", "tch")
+    model = dt.DepthModelCVHint(opts, math=math, volume_math=math)
     shapes = {k: tuple(v.shape) for k, v in model.named_parameters()}
     model.load_state_dict(syn.seeded_state_dict(shapes, 2024, 1.3), strict=False)
     model = model.to(dev)
