@@ -72,6 +72,15 @@ class TsdfIntegrateParams(C.Structure):
     ]
 
 
+class TsdfRaycastParams(C.Structure):
+    _fields_ = [
+        ("values", fp), ("weights", fp), ("dims", C.c_int32 * 3), ("origin_h", C.c_float * 3), ("voxel_size", C.c_float),
+        ("invK", fp), ("world_T_cam", fp), ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("z_near", C.c_float), ("z_far", C.c_float), ("max_steps", C.c_int32), ("weight_threshold", C.c_float),
+        ("depth_hint", fp), ("hint_mask", fp), ("sampled_weights", fp),
+    ]
+
+
 # every symbol include/doubletake_b200.h declares (tests/test_capi_symbols.py checks the header against this list)
 SYMBOLS = {
     "dtb200_abi_version": (C.c_int, []),
@@ -101,6 +110,7 @@ SYMBOLS = {
     "dtb200_relative_poses": (C.c_int, [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, fp]),
     "dtb200_exp": (C.c_int, [fp, fp, C.c_uint64, fp]),
     "dtb200_tsdf_integrate": (C.c_int, [C.POINTER(TsdfIntegrateParams), fp]),
+    "dtb200_tsdf_raycast": (C.c_int, [C.POINTER(TsdfRaycastParams), fp]),
     "dtb200_tsdf_sample": (C.c_int, [fp, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_float, fp, fp, C.c_int64, C.c_int32, fp]),
 }
 

@@ -9,8 +9,12 @@
 //
 // Thread mapping (both kernels): 4 lanes per (pixel, plane) -- lane q owns channels 4q..4q+3, so one bilinear tap is
 // ONE 16-byte load per lane and the quad reads a contiguous 64-byte NHWC texel; 8 pixels x 4 lanes = one warp.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "cv_common.cuh"
+#include "tc_common.cuh"
 
 namespace dtb200 {
 
@@ -58,22 +62,54 @@ __global__ void __launch_bounds__(kWarps * 32) cv_dot_kernel(const dtb200_cost_v
     float total = 0.f;
     bool any_d = false, any_b = false;
     const bool last = (d == p.planes - 1);
-    for (int k = 0; k < p.views; ++k) {
-      Projected pr = project_point(s_vc[k], X0, X1, X2);
-      const float* sv = p.src_feats_nhwc + ((long long)b * p.views + k) * HW * kC;
-      float4 wv = sample_quad(sv, q, pr.u, pr.v, p.height, p.width, invW, invH);
-      float dot = quad_dot(wv, cur);
-      bool depth_ok = pr.zp > 0.f;
-      dot = DT_MUL(dot, depth_ok ? 1.f : 0.f);
-      total = (k == 0) ? dot : DT_ADD(total, dot);
-      if (last && live && q == 0) {
-        bool bounds = (pr.u > 2.f) && (pr.u < (float)(p.width - 2)) && (pr.v > 2.f) && (pr.v < (float)(p.height - 2));
-        write_masks(p, b, pix, k, depth_ok, bounds, any_d, any_b);
+    // Views in groups of four: lane q of the quad does the projection / sampling setup of view 4g + q ONCE and the quad shares
+    // it by shuffles (round 1 recomputed it on all four lanes: the kernel was instruction-issue bound); then every lane
+    // gathers its 4 channels of each view with branch-free predicated taps.  Same arithmetic per (pixel, plane, view) and the
+    // same summation order over views as before: bit-identical results.
+    for (int k0 = 0; k0 < p.views; k0 += 4) {
+      SampleSetup mine;
+      mine.off = 0, mine.mask = 0, mine.w[0] = mine.w[1] = mine.w[2] = mine.w[3] = 0.f;
+      float my_m = 0.f;
+      const int my_k = k0 + q;
+      if (my_k < p.views) {
+        const Projected pr = project_point(s_vc[my_k], X0, X1, X2);
+        mine = sample_setup(pr.u, pr.v, p.height, p.width, invW, invH);
+        const bool depth_ok = pr.zp > 0.f;
+        my_m = depth_ok ? 1.f : 0.f;
+        if (last && live) {
+          const bool bounds = (pr.u > 2.f) && (pr.u < (float)(p.width - 2)) && (pr.v > 2.f) && (pr.v < (float)(p.height - 2));
+          write_masks(p, b, pix, my_k, depth_ok, bounds, any_d, any_b);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = k0 + c;
+        if (k >= p.views) break;
+        const int srcl = (lane & ~3) | c;
+        SampleSetup ss;
+        ss.off = __shfl_sync(0xffffffffu, mine.off, srcl);
+        ss.mask = __shfl_sync(0xffffffffu, mine.mask, srcl);
+        ss.w[0] = __shfl_sync(0xffffffffu, mine.w[0], srcl);
+        ss.w[1] = __shfl_sync(0xffffffffu, mine.w[1], srcl);
+        ss.w[2] = __shfl_sync(0xffffffffu, mine.w[2], srcl);
+        ss.w[3] = __shfl_sync(0xffffffffu, mine.w[3], srcl);
+        const float m = __shfl_sync(0xffffffffu, my_m, srcl);
+        const float* sv = p.src_feats_nhwc + ((long long)b * p.views + k) * HW * kC;
+        const float4 wv = sample_apply_nb(sv, q, ss, p.width);
+        const float dot = DT_MUL(quad_dot(wv, cur), m);
+        total = (k == 0) ? dot : DT_ADD(total, dot);
       }
     }
-    if (live && q == 0) {
-      p.volume[((long long)b * p.planes + d) * HW + pix] = total;
-      if (last && p.mask_any) p.mask_any[(long long)b * HW + pix] = any_d && any_b;
+    {
+      int dflag = any_d, bflag = any_b;   // the quad's lanes own different views
+      dflag |= __shfl_xor_sync(0xffffffffu, dflag, 1);
+      bflag |= __shfl_xor_sync(0xffffffffu, bflag, 1);
+      dflag |= __shfl_xor_sync(0xffffffffu, dflag, 2);
+      bflag |= __shfl_xor_sync(0xffffffffu, bflag, 2);
+      if (live && q == 0) {
+        p.volume[((long long)b * p.planes + d) * HW + pix] = total;
+        if (last && p.mask_any) p.mask_any[(long long)b * HW + pix] = (dflag && bflag) ? 1 : 0;
+      }
     }
     if (besti == 0x7fffffff || better(total, d, best, besti)) {
       best = total;
@@ -94,6 +130,195 @@ __global__ void __launch_bounds__(kWarps * 32) cv_dot_kernel(const dtb200_cost_v
         besti = i;
       }
     }
+    if (p.best_index) p.best_index[(long long)b * HW + pix] = besti;
+    if (p.lowest_cost) p.lowest_cost[(long long)b * HW + pix] = plane_depth(p, b, besti, pix);
+  }
+}
+
+// ============================================================================================================
+// DOT, TMA-staged variant (north star: "TMA-staged feature tiles into shared memory"; compared against the __ldg gather
+// above in tools/cv_sweep.py).  A block owns a 16 x 4 pixel tile and walks all (plane, view) steps.  For every step a
+// producer warp projects the tile's four corners (a projective map with z > 0 keeps the tile's image inside the convex
+// hull of the corners), and one cp.async.bulk.tensor box of kBW x kBH texels x 16 channels lands in a 4-deep shared-memory
+// ring -- the hardware zero-fills texels outside the image, i.e. grid_sample's zeros padding.  The 8 consumer warps sample
+// their bilinear taps from shared memory; a tap that falls outside the staged box (huge parallax, a corner behind the
+// camera) is fetched from global memory exactly like the kernel above, so results are bit-identical in every case.
+// ============================================================================================================
+constexpr int kTmaTW = 16, kTmaTH = 4;          // pixel tile
+constexpr int kTmaBW = 24, kTmaBH = 12;         // staged box (texels)
+constexpr int kTmaStages = 4;
+constexpr int kTmaBoxBytes = kTmaBW * kTmaBH * kC * 4;   // 18 KB
+struct DotStageMeta {
+  int bx, by, valid;
+};
+
+__global__ void __launch_bounds__(9 * 32) cv_dot_tma_kernel(const dtb200_cost_volume_params p, const __grid_constant__ CUtensorMap src_map) {
+  extern __shared__ uint8_t dsm_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsm_raw) + 127) & ~(uintptr_t)127);
+  __shared__ ViewConst s_vc[DTB200_MAX_VIEWS];
+  __shared__ DotStageMeta s_meta[kTmaStages];
+  __shared__ uint64_t s_full[kTmaStages], s_empty[kTmaStages];
+
+  const int b = blockIdx.y;
+  const int HW = p.height * p.width;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_x = ceil_div(p.width, kTmaTW);
+  const int tx0 = (blockIdx.x % tiles_x) * kTmaTW, ty0 = (blockIdx.x / tiles_x) * kTmaTH;
+  if (tid < p.views)
+    load_view_const(s_vc[tid], p.src_Ks + ((long long)b * p.views + tid) * 16, p.src_extrinsics + ((long long)b * p.views + tid) * 16,
+                    p.src_poses + ((long long)b * p.views + tid) * 16);
+  if (tid == 0) {
+    for (int s = 0; s < kTmaStages; ++s) tc::mbar_init(&s_full[s], 1), tc::mbar_init(&s_empty[s], 8);
+    tc::fence_mbar_init();
+  }
+  __syncthreads();
+  const int steps = p.planes * p.views;
+  const float invW = 1.f / (float)p.width, invH = 1.f / (float)p.height;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ producer: corner projection -> box origin -> TMA
+    const int cx = tx0 + ((lane & 1) ? min(kTmaTW, p.width - tx0) - 1 : 0);
+    const int cy = ty0 + ((lane & 2) ? min(kTmaTH, p.height - ty0) - 1 : 0);
+    float r[3];
+    backproject_ray(p.cur_invK + b * 16, cx, cy, r);
+    for (int s = 0; s < steps; ++s) {
+      const int st = s % kTmaStages;
+      tc::mbar_wait(&s_empty[st], (uint32_t)(((s / kTmaStages) & 1) ^ 1), 90, 32);
+      const int d = s / p.views, k = s - d * p.views;
+      // per-pixel planes: the corner's own plane depth (the bound is a heuristic there; the fallback path keeps it exact)
+      const float depth = plane_depth(p, b, d, min(cy, p.height - 1) * p.width + min(cx, p.width - 1));
+      const Projected pr = project_point(s_vc[k], DT_MUL(depth, r[0]), DT_MUL(depth, r[1]), DT_MUL(depth, r[2]));
+      const float ix = pr.u - 0.5f, iy = pr.v - 0.5f;
+      bool ok = (lane < 4) ? (pr.zp > 1e-6f && fabsf(ix) < 1e6f && fabsf(iy) < 1e6f) : true;
+      float xmin = lane < 4 ? ix : 3e38f, xmax = lane < 4 ? ix : -3e38f, ymin = lane < 4 ? iy : 3e38f, ymax = lane < 4 ? iy : -3e38f;
+#pragma unroll
+      for (int o = 1; o < 4; o <<= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)), xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)), ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+      }
+      ok = __all_sync(0xffffffffu, ok);
+      if (lane == 0) {
+        int bx = 0, by = 0, valid = 0;
+        if (ok) {
+          bx = (int)floorf(xmin) - 1, by = (int)floorf(ymin) - 1;
+          valid = ((int)floorf(xmax) + 2 - bx < kTmaBW) && ((int)floorf(ymax) + 2 - by < kTmaBH) ? 1 : 0;
+          // a box entirely outside the image would be all zeros: skip the copy, the consumers' range tests already give 0
+          if (bx >= p.width || by >= p.height || bx + kTmaBW <= 0 || by + kTmaBH <= 0) valid = 0;
+        }
+        s_meta[st].bx = bx, s_meta[st].by = by, s_meta[st].valid = valid;
+        if (valid) {
+          tc::mbar_arrive_expect_tx(&s_full[st], kTmaBoxBytes);
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                  tc::smem_u32(ring + (size_t)st * kTmaBoxBytes)),
+              "l"(&src_map), "r"(0), "r"(bx), "r"(by), "r"(b * p.views + k), "r"(tc::smem_u32(&s_full[st]))
+              : "memory");
+        } else {
+          tc::mbar_arrive(&s_full[st]);   // meta only (the release of the arrive orders the s_meta stores)
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers: 64 pixels x 4 channel quads
+  const int q = lane & 3;
+  const int pi = tid >> 2;
+  const int x = tx0 + (pi & 15), y = ty0 + (pi >> 4);
+  const bool live = x < p.width && y < p.height;
+  const int xc = min(x, p.width - 1), yc = min(y, p.height - 1);
+  const int pixc = yc * p.width + xc, pix = pixc;
+  float r[3];
+  backproject_ray(p.cur_invK + b * 16, xc, yc, r);
+  float4 cur;
+  {
+    const float* c = p.cur_feats + ((long long)b * kC + q * 4) * HW + pixc;
+    cur = make_float4(c[0], c[HW], c[2 * HW], c[3 * HW]);
+  }
+  float best = 0.f;
+  int besti = 0x7fffffff;
+  int s = 0;
+  for (int d = 0; d < p.planes; ++d) {
+    const float depth = plane_depth(p, b, d, pixc);
+    const float X0 = DT_MUL(depth, r[0]), X1 = DT_MUL(depth, r[1]), X2 = DT_MUL(depth, r[2]);
+    float total = 0.f;
+    bool any_d = false, any_b = false;
+    const bool last = (d == p.planes - 1);
+    for (int k0 = 0; k0 < p.views; k0 += 4) {
+      SampleSetup mine;
+      mine.off = 0, mine.mask = 0, mine.w[0] = mine.w[1] = mine.w[2] = mine.w[3] = 0.f;
+      float my_m = 0.f;
+      int my_x0 = 0, my_y0 = 0;   // texel of the nw tap (may be -1: the flat offset alone cannot tell x = -1 from x = W - 1)
+      const int my_k = k0 + q;
+      if (my_k < p.views) {
+        const Projected pr = project_point(s_vc[my_k], X0, X1, X2);
+        mine = sample_setup(pr.u, pr.v, p.height, p.width, invW, invH);
+        if (mine.mask) {  // the same expressions sample_setup evaluates
+          const float gx = DT_SUB(DT_MUL(DT_MUL(2.f, pr.u), invW), 1.f), gy = DT_SUB(DT_MUL(DT_MUL(2.f, pr.v), invH), 1.f);
+          my_x0 = (int)floorf(DT_MUL(DT_SUB(DT_MUL(DT_ADD(gx, 1.f), (float)p.width), 1.f), 0.5f));
+          my_y0 = (int)floorf(DT_MUL(DT_SUB(DT_MUL(DT_ADD(gy, 1.f), (float)p.height), 1.f), 0.5f));
+        }
+        const bool depth_ok = pr.zp > 0.f;
+        my_m = depth_ok ? 1.f : 0.f;
+        if (last && live) {
+          const bool bounds = (pr.u > 2.f) && (pr.u < (float)(p.width - 2)) && (pr.v > 2.f) && (pr.v < (float)(p.height - 2));
+          write_masks(p, b, pix, my_k, depth_ok, bounds, any_d, any_b);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = k0 + c;
+        if (k >= p.views) break;
+        const int srcl = (lane & ~3) | c;
+        SampleSetup ss;
+        const int x0t = __shfl_sync(0xffffffffu, my_x0, srcl), y0t = __shfl_sync(0xffffffffu, my_y0, srcl);
+        ss.mask = __shfl_sync(0xffffffffu, mine.mask, srcl);
+        ss.w[0] = __shfl_sync(0xffffffffu, mine.w[0], srcl);
+        ss.w[1] = __shfl_sync(0xffffffffu, mine.w[1], srcl);
+        ss.w[2] = __shfl_sync(0xffffffffu, mine.w[2], srcl);
+        ss.w[3] = __shfl_sync(0xffffffffu, mine.w[3], srcl);
+        const float m = __shfl_sync(0xffffffffu, my_m, srcl);
+        const int st = s % kTmaStages;
+        tc::mbar_wait(&s_full[st], (uint32_t)((s / kTmaStages) & 1), 91);
+        const int bx = s_meta[st].bx, by = s_meta[st].by, valid = s_meta[st].valid;
+        const float* box = reinterpret_cast<const float*>(ring + (size_t)st * kTmaBoxBytes);
+        const float* sv = p.src_feats_nhwc + ((long long)b * p.views + k) * HW * kC;
+        const bool v0 = ss.mask & 1, v1 = ss.mask & 2, v2 = ss.mask & 4, v3 = ss.mask & 8;
+        const float w0 = v0 ? ss.w[0] : 0.f, w1 = v1 ? ss.w[1] : 0.f, w2 = v2 ? ss.w[2] : 0.f, w3 = v3 ? ss.w[3] : 0.f;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto tap = [&](bool on, int dx, int dy) -> float4 {
+          if (!on) return z;
+          const int lx = x0t + dx - bx, ly = y0t + dy - by;
+          if (valid && lx >= 0 && lx < kTmaBW && ly >= 0 && ly < kTmaBH)
+            return *reinterpret_cast<const float4*>(box + ((size_t)(ly * kTmaBW + lx)) * kC + q * 4);
+          return __ldg(reinterpret_cast<const float4*>(sv + ((long long)(y0t + dy) * p.width + x0t + dx) * kC + q * 4));
+        };
+        const float4 t0 = tap(v0, 0, 0), t1 = tap(v1, 1, 0), t2 = tap(v2, 0, 1), t3 = tap(v3, 1, 1);
+        float4 wv;
+        wv.x = DT_FMA(t3.x, w3, DT_FMA(t2.x, w2, DT_FMA(t1.x, w1, DT_FMA(t0.x, w0, 0.f))));
+        wv.y = DT_FMA(t3.y, w3, DT_FMA(t2.y, w2, DT_FMA(t1.y, w1, DT_FMA(t0.y, w0, 0.f))));
+        wv.z = DT_FMA(t3.z, w3, DT_FMA(t2.z, w2, DT_FMA(t1.z, w1, DT_FMA(t0.z, w0, 0.f))));
+        wv.w = DT_FMA(t3.w, w3, DT_FMA(t2.w, w2, DT_FMA(t1.w, w1, DT_FMA(t0.w, w0, 0.f))));
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&s_empty[st]);
+        ++s;
+        const float dot = DT_MUL(quad_dot(wv, cur), m);
+        total = (k == 0) ? dot : DT_ADD(total, dot);
+      }
+    }
+    int dflag = any_d, bflag = any_b;
+    dflag |= __shfl_xor_sync(0xffffffffu, dflag, 1);
+    bflag |= __shfl_xor_sync(0xffffffffu, bflag, 1);
+    dflag |= __shfl_xor_sync(0xffffffffu, dflag, 2);
+    bflag |= __shfl_xor_sync(0xffffffffu, bflag, 2);
+    if (live && q == 0) {
+      p.volume[((long long)b * p.planes + d) * HW + pix] = total;
+      if (last && p.mask_any) p.mask_any[(long long)b * HW + pix] = (dflag && bflag) ? 1 : 0;
+    }
+    if (besti == 0x7fffffff || better(total, d, best, besti)) best = total, besti = d;
+  }
+  if (live && q == 0) {
     if (p.best_index) p.best_index[(long long)b * HW + pix] = besti;
     if (p.lowest_cost) p.lowest_cost[(long long)b * HW + pix] = plane_depth(p, b, besti, pix);
   }
@@ -398,6 +623,47 @@ uint64_t cost_volume_tch_workspace_bytes(const dtb200_cost_volume_params& p);   
 
 }  // namespace dtb200
 
+namespace dtb200 {
+
+// development / measurement switch (tools/cv_sweep.py): DTB200_CV_DOT_VARIANT=tma selects the TMA-staged dot-product kernel
+static int dot_variant() {
+  const char* e = getenv("DTB200_CV_DOT_VARIANT");   // read per launch: the sweep tool switches it between points
+  return (e && e[0] == 't') ? 1 : 0;
+}
+
+static int launch_cv_dot_tma(const dtb200_cost_volume_params& p, cudaStream_t stream) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult q;
+    void* ptr = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess) encode = (EncodeFn)ptr;
+  }
+  if (!encode) return fail(DTB200_ERR_CUDA, "cost volume (dot, tma): cuTensorMapEncodeTiled entry point not available%s");
+  CUtensorMap map;
+  cuuint64_t dims[4] = {(cuuint64_t)kC, (cuuint64_t)p.width, (cuuint64_t)p.height, (cuuint64_t)p.batch * p.views};
+  cuuint64_t strides[3] = {(cuuint64_t)kC * 4, (cuuint64_t)p.width * kC * 4, (cuuint64_t)p.height * p.width * kC * 4};
+  cuuint32_t box[4] = {(cuuint32_t)kC, kTmaBW, kTmaBH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.src_feats_nhwc), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DTB200_ERR_CUDA, "cost volume (dot, tma): cuTensorMapEncodeTiled failed with code %s%lld", "", (long long)r);
+  const size_t smem = (size_t)kTmaStages * kTmaBoxBytes + 128;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(cv_dot_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  dim3 grid(ceil_div(p.width, kTmaTW) * ceil_div(p.height, kTmaTH), p.batch);
+  cv_dot_tma_kernel<<<grid, 9 * 32, smem, stream>>>(p, map);
+  return check_launch("cv_dot_tma_kernel");
+}
+
+}  // namespace dtb200
+
 using namespace dtb200;
 
 extern "C" uint64_t dtb200_cost_volume_workspace_bytes(const dtb200_cost_volume_params* p) {
@@ -430,6 +696,7 @@ extern "C" int dtb200_cost_volume(const dtb200_cost_volume_params* pp, dtb200_st
       !p.plane_depths || !p.volume)
     return fail(DTB200_ERR_INVALID, "cost volume: null tensor pointer%s");
   const int HW = p.height * p.width;
+  if (p.kind == DTB200_VOLUME_DOT && dot_variant() == 1) return launch_cv_dot_tma(p, stream);
   if (p.kind == DTB200_VOLUME_DOT) {
     // plane split: keep >= ~4 blocks of 8 warps per SM in flight when the map is small
     long long pixel_groups = (long long)ceil_div(HW, kPixPerWarp) * p.batch;

@@ -161,23 +161,28 @@ __global__ void __launch_bounds__(256) tsdf_integrate_kernel(const dtb200_tsdf_i
   }
 }
 
-// TSDF.sample_tsdf, CPU branch (:291-337): fp32 coordinates, align_corners=True, zeros padding.
-__global__ void tsdf_sample_kernel(const __half* __restrict__ volume, int X, int Y, int Z, float ox, float oy, float oz,
-                                   float voxel_size, const float* __restrict__ pts, float* __restrict__ out, long long n,
-                                   int mode) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float o[3] = {ox, oy, oz};
-  const int dims[3] = {X, Y, Z};
-  float idx[3];
+// One sample of TSDF.sample_tsdf's arithmetic (tools/tsdf.py:291-337, CPU branch: fp32 coordinates, align_corners=True, zeros
+// padding) at world point `pt`: mode 0 = trilinear in ATen's corner order, 1 = nearest.  Shared by the sample kernel and the
+// ray caster, so a ray-cast weight is bit-identical to sample_tsdf at the same point.
+struct TsdfGrid {
+  int X, Y, Z;
+  float o[3];
+  float voxel_size;
+};
+__device__ __forceinline__ void tsdf_index(const TsdfGrid& g, const float pt[3], float idx[3]) {
+  const int dims[3] = {g.X, g.Y, g.Z};
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    float v = DT_SUB(pts[i * 3 + a], o[a]);
-    v = DT_DIV(v, voxel_size);
+    float v = DT_SUB(pt[a], g.o[a]);
+    v = DT_DIV(v, g.voxel_size);
     v = DT_DIV(v, (float)(dims[a] - 1));
-    const float g = DT_SUB(DT_MUL(v, 2.f), 1.f);
-    idx[a] = DT_MUL(DT_DIV(DT_ADD(g, 1.f), 2.f), (float)(dims[a] - 1));  // align_corners=True un-normalisation
+    const float gg = DT_SUB(DT_MUL(v, 2.f), 1.f);
+    idx[a] = DT_MUL(DT_DIV(DT_ADD(gg, 1.f), 2.f), (float)(dims[a] - 1));  // align_corners=True un-normalisation
   }
+}
+__device__ __forceinline__ float tsdf_sample_at(const __half* __restrict__ volume, const TsdfGrid& g, const float idx[3], int mode,
+                                                float* min_corner = nullptr) {
+  const int X = g.X, Y = g.Y, Z = g.Z;
   auto fetch = [&](float a0, float a1, float a2, float& v) -> bool {  // volume axis 0 / 1 / 2 index, zeros padding
     if (!(a0 >= 0.f && a0 <= (float)(X - 1) && a1 >= 0.f && a1 <= (float)(Y - 1) && a2 >= 0.f && a2 <= (float)(Z - 1))) return false;
     v = __half2float(volume[((long long)(int)a0 * Y + (int)a1) * Z + (int)a2]);
@@ -185,8 +190,7 @@ __global__ void tsdf_sample_kernel(const __half* __restrict__ volume, int X, int
   };
   if (mode == 1) {
     float v = 0.f;
-    out[i] = fetch(rintf(idx[0]), rintf(idx[1]), rintf(idx[2]), v) ? v : 0.f;
-    return;
+    return fetch(rintf(idx[0]), rintf(idx[1]), rintf(idx[2]), v) ? v : 0.f;
   }
   // grid_sample's x is the LAST volume axis (the reference swaps the point's components, :309): x = axis 2, z = axis 0
   const float x = idx[2], y = idx[1], z = idx[0];
@@ -194,10 +198,15 @@ __global__ void tsdf_sample_kernel(const __half* __restrict__ volume, int X, int
   const float x1 = DT_ADD(x0, 1.f), y1 = DT_ADD(y0, 1.f), z1 = DT_ADD(z0, 1.f);
   const float wx0 = DT_SUB(x1, x), wx1 = DT_SUB(x, x0), wy0 = DT_SUB(y1, y), wy1 = DT_SUB(y, y0);
   const float wz0 = DT_SUB(z1, z), wz1 = DT_SUB(z, z0);
-  float acc = 0.f;
+  float acc = 0.f, lo = 3e38f;
   auto corner = [&](float cx, float cy, float cz, float wx, float wy, float wz) {
     float v;
-    if (fetch(cz, cy, cx, v)) acc = DT_ADD(acc, DT_MUL(v, DT_MUL(DT_MUL(wx, wy), wz)));
+    if (fetch(cz, cy, cx, v)) {
+      acc = DT_ADD(acc, DT_MUL(v, DT_MUL(DT_MUL(wx, wy), wz)));
+      lo = fminf(lo, v);
+    } else {
+      lo = fminf(lo, 0.f);   // a corner in the zero padding counts as unobserved
+    }
   };
   // ATen grid_sampler_3d order: tnw, tne, tsw, tse, bnw, bne, bsw, bse
   corner(x0, y0, z0, wx0, wy0, wz0);
@@ -208,7 +217,100 @@ __global__ void tsdf_sample_kernel(const __half* __restrict__ volume, int X, int
   corner(x1, y0, z1, wx1, wy0, wz1);
   corner(x0, y1, z1, wx0, wy1, wz1);
   corner(x1, y1, z1, wx1, wy1, wz1);
-  out[i] = acc;
+  if (min_corner) *min_corner = lo;
+  return acc;
+}
+
+__global__ void tsdf_sample_kernel(const __half* __restrict__ volume, TsdfGrid g, const float* __restrict__ pts, float* __restrict__ out,
+                                   long long n, int mode) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float pt[3] = {pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2]};
+  float idx[3];
+  tsdf_index(g, pt, idx);
+  out[i] = tsdf_sample_at(volume, g, idx, mode);
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Rendered-depth hint by ray casting the TSDF (the mesh-free form): replaces, for the incremental loop
+// of reference test_incremental.py:186-252, marching cubes (tools/marching_cubes/marching_cubes.cu) + the PyTorch3D depth
+// rasteriser (utils/rendering_utils.py:25-53) + BackprojectDepth + TSDF.sample_tsdf + the threshold / NaN / mask rules
+// (:238-252) by ONE kernel: one thread per hint pixel marches its camera ray through the volume, stops at the first
+// front-facing zero crossing between two OBSERVED samples (all eight voxels around either sample carry a weight > 0 -- the
+// reference meshes only cubes of active voxels, and a trilinear blend of observed and never-observed (-1) voxels would
+// fake a crossing at every frustum boundary), interpolates the crossing depth, samples the fused confidence there with sample_tsdf's exact arithmetic,
+// and writes depth_hint_b1hw (NaN where there is no surface or the confidence is below the threshold),
+// depth_hint_mask_b1hw and sampled_weights_b1hw (0 where invalid).
+// Marching rule (restated by oracle/oracle_tsdf.py::raycast_hint): start at z_near; step 2 voxels while |tsdf| >= 0.99 or the
+// sample is outside the volume / unobserved, half a voxel otherwise (the truncation band is +-3 voxels wide, so a 2-voxel
+// step cannot jump over it); depth is the camera-space z of the crossing, z* = z0 + (z1 - z0) * v0 / (v0 - v1).
+// ----------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ray_point(const float* ray, const float* Rt, float z, float pt[3]) {
+  const float c0 = DT_MUL(z, ray[0]), c1 = DT_MUL(z, ray[1]), c2 = DT_MUL(z, ray[2]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float acc = DT_MUL(Rt[i * 4 + 0], c0);
+    acc = DT_FMA(Rt[i * 4 + 1], c1, acc);
+    acc = DT_FMA(Rt[i * 4 + 2], c2, acc);
+    pt[i] = DT_ADD(acc, Rt[i * 4 + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(128) tsdf_raycast_kernel(const dtb200_tsdf_raycast_params p, TsdfGrid g) {
+  const int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 8 + (threadIdx.x >> 4);
+  const int b = blockIdx.z;
+  if (x >= p.width || y >= p.height) return;
+  const __half* values = reinterpret_cast<const __half*>(p.values);
+  const __half* weights = reinterpret_cast<const __half*>(p.weights);
+  const float* invK = p.invK + b * 16;
+  const float* Rt = p.world_T_cam + b * 16;
+  float ray[3];
+  {
+    const float px = (float)x + 0.5f, py = (float)y + 0.5f;   // pixel centres, BackprojectDepth (utils/geometry_utils.py:34-39)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float acc = DT_MUL(invK[i * 4 + 0], px);
+      acc = DT_FMA(invK[i * 4 + 1], py, acc);
+      ray[i] = DT_ADD(acc, invK[i * 4 + 2]);
+    }
+  }
+  const float big_step = DT_MUL(2.f, g.voxel_size), small_step = DT_MUL(0.5f, g.voxel_size);
+  float z = p.z_near, z_prev = 0.f, v_prev = -1.f, w_prev = 0.f;
+  float hit = -1.f;
+  for (int it = 0; it < p.max_steps && z <= p.z_far; ++it) {
+    float pt[3], idx[3];
+    ray_point(ray, Rt, z, pt);
+    tsdf_index(g, pt, idx);
+    const bool inside = idx[0] >= 0.f && idx[0] <= (float)(g.X - 1) && idx[1] >= 0.f && idx[1] <= (float)(g.Y - 1) && idx[2] >= 0.f &&
+                        idx[2] <= (float)(g.Z - 1);
+    float v = -1.f, w = 0.f;
+    if (inside) {
+      float w_min;
+      tsdf_sample_at(weights, g, idx, 0, &w_min);
+      if (w_min > 0.f) w = 1.f, v = tsdf_sample_at(values, g, idx, 0);   // w: "observed" flag of this sample
+    }
+    if (v_prev > 0.f && v <= 0.f && w_prev > 0.f && w > 0.f) {
+      hit = DT_ADD(z_prev, DT_DIV(DT_MUL(DT_SUB(z, z_prev), v_prev), DT_SUB(v_prev, v)));
+      break;
+    }
+    z_prev = z, v_prev = v, w_prev = w;
+    z = DT_ADD(z, fabsf(v) >= 0.99f ? big_step : small_step);
+  }
+  const long long o = ((long long)b * p.height + y) * p.width + x;
+  float hint = __int_as_float(0x7fc00000), sw = 0.f;
+  if (hit > 0.f) {
+    float pt[3], idx[3];
+    ray_point(ray, Rt, hit, pt);
+    tsdf_index(g, pt, idx);
+    sw = tsdf_sample_at(weights, g, idx, 0);
+    // test_incremental.py:238-252: depth = camera z of the rendered point; hint[weights < threshold] = NaN; mask = ~isnan;
+    // weights[~mask] = 0
+    if (!(sw < p.weight_threshold)) hint = DT_MUL(hit, ray[2]);
+    else sw = 0.f;
+  }
+  p.depth_hint[o] = hint;
+  p.hint_mask[o] = isnan(hint) ? 0.f : 1.f;
+  p.sampled_weights[o] = isnan(hint) ? 0.f : sw;
 }
 
 }  // namespace dtb200
@@ -257,8 +359,27 @@ extern "C" int dtb200_tsdf_sample(const void* volume, const int32_t* dims, const
   if (dims[0] < 2 || dims[1] < 2 || dims[2] < 2) return fail(DTB200_ERR_INVALID, "tsdf_sample: volume dims must be >= 2%s");
   if (num_points <= 0) return DTB200_OK;
   const long long blocks = (num_points + 255) / 256;
+  TsdfGrid g;
+  g.X = dims[0], g.Y = dims[1], g.Z = dims[2];
+  g.o[0] = origin_h[0], g.o[1] = origin_h[1], g.o[2] = origin_h[2];
+  g.voxel_size = voxel_size;
   tsdf_sample_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half*>(volume), dims[0], dims[1], dims[2], origin_h[0], origin_h[1], origin_h[2], voxel_size,
-      world_points, out, (long long)num_points, mode);
+      reinterpret_cast<const __half*>(volume), g, world_points, out, (long long)num_points, mode);
   return check_launch("tsdf_sample_kernel");
+}
+
+extern "C" int dtb200_tsdf_raycast(const dtb200_tsdf_raycast_params* p, dtb200_stream_t stream) {
+  if (!p || !p->values || !p->weights || !p->invK || !p->world_T_cam || !p->depth_hint || !p->hint_mask || !p->sampled_weights)
+    return fail(DTB200_ERR_INVALID, "tsdf_raycast: null argument%s");
+  if (p->batch < 1 || p->height < 1 || p->width < 1) return fail(DTB200_ERR_INVALID, "tsdf_raycast: bad image size%s");
+  if (p->dims[0] < 2 || p->dims[1] < 2 || p->dims[2] < 2) return fail(DTB200_ERR_INVALID, "tsdf_raycast: volume dims must be >= 2%s");
+  if (!(p->voxel_size > 0.f) || !(p->z_near > 0.f) || !(p->z_far > p->z_near) || p->max_steps < 1)
+    return fail(DTB200_ERR_INVALID, "tsdf_raycast: bad voxel size / depth range / step bound%s");
+  TsdfGrid g;
+  g.X = p->dims[0], g.Y = p->dims[1], g.Z = p->dims[2];
+  g.o[0] = p->origin_h[0], g.o[1] = p->origin_h[1], g.o[2] = p->origin_h[2];
+  g.voxel_size = p->voxel_size;
+  dim3 grid((p->width + 15) / 16, (p->height + 7) / 8, p->batch);
+  tsdf_raycast_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p, g);
+  return check_launch("tsdf_raycast_kernel");
 }

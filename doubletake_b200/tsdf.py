@@ -6,7 +6,8 @@ for the next keyframe's hint (``TSDF.sample_tsdf``, :277-337; test_incremental.p
 Same class names, constructor arguments, method signatures and ``.npz`` format as the reference.  The volume lives in HBM
 as the reference's fp16 tensors; ``integrate_depth`` is ONE CUDA kernel per batch of up to 8 frames
 (``csrc/tsdf.cu``), ``sample_tsdf`` one kernel.  No CPU fallback: ``use_gpu=False`` raises.
-Mesh extraction (``to_mesh*``, marching cubes) is row N3 and not part of this engine yet.
+Row N3 (hint rendering) is served WITHOUT a mesh: ``TSDF.render_depth_hint`` ray-casts the volume in one kernel and emits
+the three hint tensors of the incremental loop; ``to_mesh*`` (marching cubes for mesh export) is not part of the engine.
 
 Numerics: the kernels reproduce the reference's fp16 torch ops rounding for rounding.  fp16 ``grid_sample`` behaves
 differently in ATen's CPU and CUDA builds (index arithmetic precision, non-finite indices); ``semantics="aten_cuda"``
@@ -143,9 +144,39 @@ class TSDF:
             voxel_coords_3hwd=self.voxel_coords_3hwd.cpu().numpy().astype(np.float16), voxel_size=self.voxel_size)
 
     def to_mesh(self, *a, **k):
-        raise NotImplementedError("mesh extraction (marching cubes) is SURVEY.md §8f row N3, not part of doubletake_b200 yet")
+        raise NotImplementedError("doubletake_b200 renders the depth hint by ray casting the TSDF (render_depth_hint); "
+                                  "mesh extraction for export (marching cubes) is not part of the engine")
 
     to_mesh_pytorch3d = save_mesh = to_mesh
+
+    def render_depth_hint(self, world_T_cam_b44, invK_b44, height, width, z_near=0.05, z_far=10.0, weight_threshold=0.025,
+                          max_steps=4096):
+        """The rendered-depth hint of the incremental loop (reference test_incremental.py:186-252) without a mesh: ONE
+        kernel ray-casts the fused TSDF from the current camera and returns the three tensors ``DepthModelCVHint.forward``
+        consumes -- ``depth_hint_b1hw`` (NaN where no surface is seen or the fused confidence is below
+        ``weight_threshold``), ``depth_hint_mask_b1hw`` (float 0/1) and ``sampled_weights_b1hw`` (0 where invalid) --
+        plus the boolean ``depth_hint_mask_b_b1hw`` the reference keeps next to them.  It replaces
+        ``fuser.get_mesh_pytorch3d`` (marching cubes), ``PyTorch3DMeshDepthRenderer.render``, ``BackprojectDepth``,
+        ``fuser.sample_tsdf(..., "weights")`` and the masking lines :238-252.  ``invK_b44``: inverse intrinsics at the hint
+        resolution (``cur_data["invK_s0_b44"]``); poses may live on the host or on the device."""
+        self.cuda()
+        dev = self.tsdf_values.device
+        invK = L.f32(invK_b44, dev)
+        pose = L.f32(world_T_cam_b44, dev)
+        B = pose.shape[0]
+        out = [torch.empty((B, 1, height, width), dtype=torch.float32, device=dev) for _ in range(3)]
+        p = L.TsdfRaycastParams()
+        p.values, p.weights = L.ptr(self.tsdf_values.contiguous()), L.ptr(self.tsdf_weights.contiguous())
+        p.dims = (C.c_int32 * 3)(*self.tsdf_values.shape)
+        p.origin_h = (C.c_float * 3)(*[float(v) for v in self.origin.float().cpu()])
+        p.voxel_size = float(self.voxel_size)
+        p.invK, p.world_T_cam = L.ptr(invK), L.ptr(pose)
+        p.batch, p.height, p.width = B, height, width
+        p.z_near, p.z_far, p.max_steps, p.weight_threshold = z_near, z_far, max_steps, weight_threshold
+        p.depth_hint, p.hint_mask, p.sampled_weights = (L.ptr(t) for t in out)
+        L.check(L.lib().dtb200_tsdf_raycast(C.byref(p), L.stream()))
+        return {"depth_hint_b1hw": out[0], "depth_hint_mask_b1hw": out[1], "depth_hint_mask_b_b1hw": out[1] > 0,
+                "sampled_weights_b1hw": out[2]}
 
     def sample_tsdf(self, world_points_N3, what_to_sample="tsdf", sampling_method="bilinear"):
         """(N,3) world points -> (N,) fp32 samples of the TSDF or the weights (tools/tsdf.py:277-337)."""
@@ -195,6 +226,10 @@ class TSDFFuser:
         self.maxW = 100.0
 
     voxel_coords_3hwd = property(lambda self: self.tsdf.voxel_coords_3hwd)
+    def render_depth_hint(self, *args, **kwargs):
+        """See ``TSDF.render_depth_hint``."""
+        return self.tsdf.render_depth_hint(*args, **kwargs)
+
     tsdf_values = property(lambda self: self.tsdf.tsdf_values)
     tsdf_weights = property(lambda self: self.tsdf.tsdf_weights)
     voxel_size = property(lambda self: self.tsdf.voxel_size)

@@ -275,6 +275,30 @@ int dtb200_tsdf_integrate(const dtb200_tsdf_integrate_params* p, dtb200_stream_t
 int dtb200_tsdf_sample(const void* volume, const int32_t* dims, const float* origin_h, float voxel_size,
                        const float* world_points, float* out, int64_t num_points, int32_t mode, dtb200_stream_t stream);
 
+/* Rendered-depth hint of the incremental loop by ray casting the fused TSDF (mesh-free): one kernel
+ * replaces reference marching cubes (tools/marching_cubes/marching_cubes.cu:164-424) + the mesh depth rasteriser
+ * (utils/rendering_utils.py:25-53) + BackprojectDepth + TSDF.sample_tsdf + the threshold / NaN / mask rules of
+ * test_incremental.py:215-252.  Per hint pixel: the first front-facing zero crossing of the TSDF along the camera ray between
+ * two observed samples, its camera-space depth, and the fused confidence sampled there exactly as dtb200_tsdf_sample does. */
+typedef struct dtb200_tsdf_raycast_params {
+  const void* values;        /* fp16 (X, Y, Z) */
+  const void* weights;       /* fp16 (X, Y, Z) */
+  int32_t dims[3];
+  float origin_h[3];         /* fp16(origin) widened, as TSDF.origin is stored */
+  float voxel_size;
+  const float* invK;         /* DEVICE (B,4,4) inverse intrinsics at the hint resolution (invK_s0_b44) */
+  const float* world_T_cam;  /* DEVICE (B,4,4) camera pose */
+  int32_t batch, height, width;
+  float z_near, z_far;       /* marching range along camera z */
+  int32_t max_steps;         /* hard bound on marching steps per ray */
+  float weight_threshold;    /* 0.025 (test_incremental.py:244) */
+  float* depth_hint;         /* (B,1,H,W): depth or NaN                 -> cur_data["depth_hint_b1hw"] */
+  float* hint_mask;          /* (B,1,H,W): 1 where depth_hint is valid   -> cur_data["depth_hint_mask_b1hw"] */
+  float* sampled_weights;    /* (B,1,H,W): confidence, 0 where invalid   -> cur_data["sampled_weights_b1hw"] */
+} dtb200_tsdf_raycast_params;
+
+int dtb200_tsdf_raycast(const dtb200_tsdf_raycast_params* p, dtb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

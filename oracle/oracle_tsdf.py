@@ -196,3 +196,92 @@ def sample_volume(vol, world_points_N3, what="weights", mode="bilinear"):
         xi, yi, zi = [np.where(ok, c, 0).astype(np.int64) for c in (cx, cy, cz)]
         out = (out + np.where(ok, volume[zi, yi, xi] * w.astype(F32), F32(0)).astype(F32)).astype(F32)
     return out
+
+
+def _index_of(vol, pts_N3):
+    """The index arithmetic of sample_volume (one rounded fp32 op per step)."""
+    dims = np.array(vol["tsdf_values"].shape, dtype=F32)
+    v = (f(pts_N3) - f(vol["origin"]).reshape(1, 3)).astype(F32)
+    v = (v / F32(vol["voxel_size"])).astype(F32)
+    v = (v / (dims.reshape(1, 3) - F32(1))).astype(F32)
+    g = (v * F32(2) - F32(1)).astype(F32)
+    return np.stack([((g[:, a] + F32(1)) / F32(2) * (dims[a] - F32(1))).astype(F32) for a in range(3)], 1), dims
+
+
+def raycast_hint(vol, invK_44, world_T_cam_44, height, width, z_near=0.05, z_far=10.0, weight_threshold=0.025, max_steps=4096):
+    """CPU restatement of the product's TSDF ray caster (csrc/tsdf.cu::tsdf_raycast_kernel) -- the reference has no ray
+    caster (it meshes the TSDF and rasterises the mesh, test_incremental.py:202-252), so this oracle pins OUR marching rule
+    operation for operation; what it shares with the reference is pinned elsewhere: the confidence at the hit point is
+    sample_volume (= TSDF.sample_tsdf, fixtures) and the threshold / NaN / mask rules are test_incremental.py:238-252.
+    Vectorised over pixels: every ray carries its own state, finished rays are masked out.
+    Returns (depth_hint with NaN, mask float, sampled_weights) of shape (height, width)."""
+    invK, Rt = f(invK_44), f(world_T_cam_44)
+    ys, xs = np.meshgrid(np.arange(height), np.arange(width), indexing="ij")
+    px, py = (xs.reshape(-1).astype(F32) + F32(0.5)), (ys.reshape(-1).astype(F32) + F32(0.5))
+    fma = lambda a, b, c: (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(F32)  # noqa: E731  (one rounding)
+    ray = np.stack([(fma(py, invK[i, 1], (invK[i, 0] * px).astype(F32)) + invK[i, 2]).astype(F32) for i in range(3)], 1)
+    vs = F32(vol["voxel_size"])
+    big, small = (F32(2) * vs).astype(F32), (F32(0.5) * vs).astype(F32)
+    n = len(px)
+
+    def point(z, sel):
+        c = (z[:, None] * ray[sel]).astype(F32)
+        out = []
+        for i in range(3):
+            acc = (Rt[i, 0] * c[:, 0]).astype(F32)
+            acc = fma(c[:, 1], Rt[i, 1], acc)
+            acc = fma(c[:, 2], Rt[i, 2], acc)
+            out.append((acc + Rt[i, 3]).astype(F32))
+        return np.stack(out, 1)
+
+    def sample(what, idx):
+        volume = f(vol["tsdf_values"] if what == "tsdf" else vol["tsdf_weights"])
+        dims = volume.shape
+        x, y, z = idx[:, 2], idx[:, 1], idx[:, 0]
+        x0, y0, z0 = np.floor(x), np.floor(y), np.floor(z)
+        x1, y1, z1 = x0 + 1, y0 + 1, z0 + 1
+        out = np.zeros(len(idx), F32)
+        lo = np.full(len(idx), F32(3e38), F32)
+        for cx, cy, cz, wx, wy, wz in ((x0, y0, z0, x1 - x, y1 - y, z1 - z), (x1, y0, z0, x - x0, y1 - y, z1 - z),
+                                       (x0, y1, z0, x1 - x, y - y0, z1 - z), (x1, y1, z0, x - x0, y - y0, z1 - z),
+                                       (x0, y0, z1, x1 - x, y1 - y, z - z0), (x1, y0, z1, x - x0, y1 - y, z - z0),
+                                       (x0, y1, z1, x1 - x, y - y0, z - z0), (x1, y1, z1, x - x0, y - y0, z - z0)):
+            ok = (cx >= 0) & (cx <= dims[2] - 1) & (cy >= 0) & (cy <= dims[1] - 1) & (cz >= 0) & (cz <= dims[0] - 1)
+            xi, yi, zi = [np.where(ok, c, 0).astype(np.int64) for c in (cx, cy, cz)]
+            w = ((wx.astype(F32) * wy.astype(F32)).astype(F32) * wz.astype(F32)).astype(F32)
+            out = (out + np.where(ok, (volume[zi, yi, xi] * w).astype(F32), F32(0))).astype(F32)
+            lo = np.minimum(lo, np.where(ok, volume[zi, yi, xi], F32(0)))
+        return out, lo
+
+    z = np.full(n, F32(z_near), F32)
+    z_prev, v_prev, w_prev = np.zeros(n, F32), np.full(n, F32(-1), F32), np.zeros(n, F32)
+    hit = np.full(n, F32(-1), F32)
+    active = np.ones(n, bool)
+    for _ in range(max_steps):
+        active &= z <= F32(z_far)
+        if not active.any():
+            break
+        a = np.nonzero(active)[0]
+        idx, dims = _index_of(vol, point(z[a], a))
+        inside = np.all((idx >= 0) & (idx <= dims.reshape(1, 3) - 1), 1)
+        # "observed" sample: all eight surrounding voxels carry a weight > 0 (corners in the zero padding count as 0)
+        w = (inside & (sample("weights", idx)[1] > 0)).astype(F32)
+        v = np.where(w > 0, sample("tsdf", idx)[0], F32(-1)).astype(F32)
+        cross = (v_prev[a] > 0) & (v <= 0) & (w_prev[a] > 0) & (w > 0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            zs = (z_prev[a] + (((z[a] - z_prev[a]).astype(F32) * v_prev[a]).astype(F32) / (v_prev[a] - v).astype(F32)).astype(F32)).astype(F32)
+        hit[a[cross]] = zs[cross]
+        active[a[cross]] = False
+        keep = ~cross
+        z_prev[a[keep]], v_prev[a[keep]], w_prev[a[keep]] = z[a[keep]], v[keep], w[keep]
+        z[a[keep]] = (z[a[keep]] + np.where(np.abs(v[keep]) >= F32(0.99), big, small)).astype(F32)
+    found = hit > 0
+    sw = np.zeros(n, F32)
+    if found.any():
+        idx, _ = _index_of(vol, point(hit[found], found))
+        sw[found] = sample("weights", idx)[0]
+    depth = (hit * ray[:, 2]).astype(F32)
+    valid = found & ~(sw < F32(weight_threshold))
+    hint = np.where(valid, depth, np.float32("nan")).astype(F32)
+    return (hint.reshape(height, width), valid.astype(F32).reshape(height, width),
+            np.where(valid, sw, F32(0)).astype(F32).reshape(height, width))

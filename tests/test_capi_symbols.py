@@ -50,6 +50,7 @@ def test_struct_layout_matches_header_field_order():
     assert _struct_fields("dtb200_cost_volume_params") == [f[0] for f in _lib.CostVolumeParams._fields_]
     assert _struct_fields("dtb200_tsdf_frame") == [f[0] for f in _lib.TsdfFrame._fields_]
     assert _struct_fields("dtb200_tsdf_integrate_params") == [f[0] for f in _lib.TsdfIntegrateParams._fields_]
+    assert _struct_fields("dtb200_tsdf_raycast_params") == [f[0] for f in _lib.TsdfRaycastParams._fields_]
 
 
 def test_struct_sizes_and_offsets_match_the_c_compiler(tmp_path):
@@ -58,7 +59,8 @@ def test_struct_sizes_and_offsets_match_the_c_compiler(tmp_path):
     import subprocess
 
     pairs = [("dtb200_conv_params", _lib.ConvParams), ("dtb200_cost_volume_params", _lib.CostVolumeParams),
-             ("dtb200_tsdf_frame", _lib.TsdfFrame), ("dtb200_tsdf_integrate_params", _lib.TsdfIntegrateParams)]
+             ("dtb200_tsdf_frame", _lib.TsdfFrame), ("dtb200_tsdf_integrate_params", _lib.TsdfIntegrateParams),
+             ("dtb200_tsdf_raycast_params", _lib.TsdfRaycastParams)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "doubletake_b200.h")}"',
              "int main(void) {"]
     for cname, cls in pairs:
@@ -110,3 +112,10 @@ def test_tsdf_argument_validation_without_a_gpu():
     dims, origin = (ctypes.c_int32 * 3)(16, 16, 16), (ctypes.c_float * 3)(0, 0, 0)
     assert lib.dtb200_tsdf_sample(16, dims, origin, 0.04, 16, 16, 10, 5, None) == -1 and b"mode" in lib.dtb200_last_error()
     assert lib.dtb200_tsdf_sample(None, dims, origin, 0.04, 16, 16, 10, 0, None) == -1
+    assert lib.dtb200_tsdf_raycast(None, None) == -1
+    r = _lib.TsdfRaycastParams()
+    r.values = r.weights = r.invK = r.world_T_cam = r.depth_hint = r.hint_mask = r.sampled_weights = 64
+    r.batch, r.height, r.width = 1, 4, 4
+    r.dims = (ctypes.c_int32 * 3)(16, 16, 16)
+    r.voxel_size, r.z_near, r.z_far, r.max_steps = 0.04, 1.0, 0.5, 10
+    assert lib.dtb200_tsdf_raycast(ctypes.byref(r), None) == -1 and b"depth range" in lib.dtb200_last_error()

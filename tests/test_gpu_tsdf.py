@@ -176,3 +176,89 @@ def test_reference_default_volume_lazy_grid():
     crop = (slice(lo[0], hi[0]), slice(lo[1], hi[1]), slice(lo[2], hi[2]))
     assert np.array_equal(bits(big.tsdf_values[crop]), bits(ref["tsdf_values"]))
     assert np.array_equal(bits(big.tsdf_weights[crop]), bits(ref["tsdf_weights"]))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_raycast_hint_matches_the_cpu_oracle_and_sample_tsdf(name):
+    """Row N3 without a mesh: TSDF.render_depth_hint (one kernel) against the CPU oracle of the same marching rule on the
+    reference-fused fixture volumes -- masks identical, depth and confidence bit-identical where valid -- and against the
+    reference-pinned sample_tsdf: the confidence at a hint pixel IS sample_tsdf at the back-projected hint point
+    (test_incremental.py:220-236), so the two must agree to the bit."""
+    fx = hp.load(name)
+    vol = bt.TSDF.from_bounds(case_bounds(fx), float(fx["voxel_size"]))
+    vol.tsdf_values = torch.from_numpy(fx["values"]).cuda()
+    vol.tsdf_weights = torch.from_numpy(fx["weights"]).cuda()
+    ih, iw = fx["depth"].shape[2:]
+    K = fx["K"][0].astype(np.float32)
+    invK = np.linalg.inv(K).astype(np.float32)
+    ovol = dict(tsdf_values=fx["values"], tsdf_weights=fx["weights"], origin=fx["origin"], voxel_size=float(fx["voxel_size"]))
+    for f in (0, fx["depth"].shape[0] - 1):
+        pose = np.linalg.inv(fx["cam_T_world"][f].astype(np.float32)).astype(np.float32)
+        for thr in (0.025, 0.004):
+            before = L.launch_count()
+            out = vol.render_depth_hint(torch.from_numpy(pose)[None], torch.from_numpy(invK)[None], ih, iw, weight_threshold=thr)
+            assert L.launch_count() == before + 1
+            hint, mask, sw = (out[k][0, 0].cpu().numpy() for k in ("depth_hint_b1hw", "depth_hint_mask_b1hw", "sampled_weights_b1hw"))
+            rh, rm, rw = ot.raycast_hint(ovol, invK, pose, ih, iw, weight_threshold=thr)
+            assert np.array_equal(mask, rm) and np.array_equal(np.isnan(hint), rm == 0)
+            assert np.array_equal(hint[rm > 0], rh[rm > 0]) and np.array_equal(sw, rw)
+            assert torch.equal(out["depth_hint_mask_b_b1hw"], out["depth_hint_mask_b1hw"] > 0)
+        # confidence == sample_tsdf("weights") at the back-projected hint points
+        ok = rm > 0
+        if ok.any():
+            ys, xs = np.nonzero(ok)
+            pix = np.stack([xs + 0.5, ys + 0.5, np.ones(len(xs))], 0).astype(np.float32)
+            cam = (invK[:3, :3] @ pix) * hint[ok][None]
+            world = (pose[:3, :3] @ cam + pose[:3, 3:4]).T.astype(np.float32)
+            got = vol.sample_tsdf(torch.from_numpy(np.ascontiguousarray(world)).cuda(), what_to_sample="weights").cpu().numpy()
+            assert np.allclose(got, sw[ok], rtol=0, atol=2e-4)   # the kernel's own world point differs by fp32 rounding of the matmul
+
+
+def test_incremental_loop_runs_on_device():
+    """Ten keyframes of the incremental mode (reference test_incremental.py:175-300) with nothing but this engine between
+    the encoders' outputs and the fused volume: render the hint from the TSDF (empty for the first keyframe), run
+    DepthModelCVHint.forward with it, fuse the predicted depth_pred_s0 -- no mesh, no host round trip of a tensor."""
+    import doubletake_b200 as dt
+    from doubletake_b200 import synthetic as syn
+
+    cfg = syn.CONFIGS["tiny"]
+    opts = dt.HotPathOptions(matching_num_depth_bins=cfg.planes, model_num_views=cfg.num_src + 1, image_height=cfg.image_h,
+                             image_width=cfg.image_w)
+    model = dt.DepthModelCVHint(opts, math="tch", volume_math="tch")
+    shapes = {k: tuple(v.shape) for k, v in model.named_parameters()}
+    model.load_state_dict(syn.seeded_state_dict(shapes, 77, 1.3), strict=False)
+    model = model.cuda()
+    vol = bt.TSDF.from_bounds(dict(xmin=-4.0, xmax=4.0, ymin=-4.0, ymax=4.0, zmin=-1.0, zmax=7.0), 0.08, lazy_grid=True)
+    fuser = bt.TSDFFuser(vol, max_depth=6.0)
+    rh, rw = cfg.image_h // 2, cfg.image_w // 2
+    coverage = []
+    for i in range(10):
+        inp = syn.cost_volume_inputs(cfg, seed=500 + i)
+        priors = syn.prior_features(cfg, syn._gen(900 + i))
+        pose = torch.eye(4)
+        pose[0, 3] = 0.03 * i   # the camera slides sideways
+        K_s1 = torch.linalg.inv(inp["cur_invK"][0])
+        K_s0 = K_s1.clone()
+        K_s0[:2] *= 2
+        cur = {"cam_T_world_b44": torch.linalg.inv(pose)[None], "world_T_cam_b44": pose[None], "invK_s1_b44": inp["cur_invK"],
+               "matching_feats_bchw": inp["cur_feats"], "image_prior_feats": priors}
+        src = {"cam_T_world_b44": inp["src_extrinsics"] @ torch.linalg.inv(pose), "world_T_cam_b44": pose @ inp["src_poses"],
+               "K_s1_b44": inp["src_Ks"], "matching_feats_bkchw": inp["src_feats"]}
+        if i == 0:  # test_incremental.py:260-269: empty hint
+            hint = {"depth_hint_b1hw": torch.full((1, 1, rh, rw), float("nan")), "depth_hint_mask_b1hw": torch.zeros(1, 1, rh, rw),
+                    "sampled_weights_b1hw": torch.zeros(1, 1, rh, rw)}
+        else:
+            hint = fuser.render_depth_hint(pose[None], torch.linalg.inv(K_s0)[None], rh, rw, weight_threshold=0.004)
+            coverage.append(float(hint["depth_hint_mask_b1hw"].mean()))
+            assert bool(torch.isnan(hint["depth_hint_b1hw"][hint["depth_hint_mask_b1hw"] == 0]).all())
+            assert bool((hint["sampled_weights_b1hw"][hint["depth_hint_mask_b1hw"] == 0] == 0).all())
+        cur.update({k: v for k, v in hint.items() if k != "depth_hint_mask_b_b1hw"})
+        cur = {k: ([t.cuda() for t in v] if isinstance(v, list) else v.cuda()) for k, v in cur.items()}
+        src = {k: v.cuda() for k, v in src.items()}
+        out = model("test", cur, src, return_mask=True)
+        depth = out["depth_pred_s0_b1hw"]
+        assert depth.shape == (1, 1, rh, rw) and bool(torch.isfinite(depth).all())
+        fuser.integrate_depth(depth, torch.linalg.inv(pose)[None], K_s0[None])
+    torch.cuda.synchronize()
+    assert int((vol.tsdf_weights > 0).sum()) > 1000
+    assert max(coverage) > 0.05, coverage   # later keyframes do see the surface fused from the earlier ones

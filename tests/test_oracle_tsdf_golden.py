@@ -177,3 +177,38 @@ def test_index_box_margin_follows_the_fp16_ulp_far_from_the_origin():
         idx = np.argwhere(inside)
         if len(idx):
             assert all(idx[:, a].min() >= begin[a] and idx[:, a].max() < end[a] for a in range(3)), (lo, hi, begin, end)
+
+
+def test_raycast_oracle_recovers_a_fused_plane():
+    """The hint renderer's CPU oracle (oracle_tsdf.raycast_hint = the product's marching rule, operation for operation):
+    fuse a tilted plane four times, ray-cast it from the fusing camera and from a second, rotated and shifted one -- the
+    rendered depth is the analytic ray/plane intersection to a fraction of a voxel, no pixel fakes a surface at a frustum
+    boundary, and the default 0.025 confidence threshold of test_incremental.py:244 rejects these few-observation surfaces."""
+    bounds = dict(xmin=-1.0, xmax=1.0, ymin=-0.8, ymax=0.8, zmin=0.2, zmax=2.8)
+    vol = ot.volume_from_bounds(bounds, 0.04)
+    ih, iw = 48, 64
+    K = np.eye(4, dtype=np.float32)
+    K[0, 0] = K[1, 1] = 60.0
+    K[0, 2], K[1, 2] = iw / 2, ih / 2
+    ys, xs = np.meshgrid(np.arange(ih), np.arange(iw), indexing="ij")
+    rx, ry = (xs + 0.5 - K[0, 2]) / K[0, 0], (ys + 0.5 - K[1, 2]) / K[1, 1]
+    depth = (2.0 / (1 - 0.2 * rx)).astype(np.float32)   # the plane z = 2 + 0.2 x seen from the origin
+    T = np.eye(4, dtype=np.float32)
+    for _ in range(4):
+        ot.integrate_depth(vol, depth[None, None].astype(np.float16), T[None].astype(np.float16), K[None].astype(np.float16),
+                           min_depth=0.5, max_depth=3.0)
+    hint, mask, sw = ot.raycast_hint(vol, np.linalg.inv(K), T, ih, iw, weight_threshold=0.005)
+    ok = mask > 0
+    assert ok.mean() > 0.8 and np.isnan(hint[~ok]).all() and (sw[~ok] == 0).all()
+    assert np.abs(hint[ok] - depth[ok]).max() < 0.25 * 0.04
+    ang = np.deg2rad(8)
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float32)
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, :3], pose[:3, 3] = R, [0.15, 0.02, 0.1]
+    hint2, mask2, _ = ot.raycast_hint(vol, np.linalg.inv(K), pose, ih, iw, weight_threshold=0.005)
+    dirs = np.stack([rx, ry, np.ones_like(rx)], -1) @ R.T
+    t = (2 + 0.2 * pose[0, 3] - pose[2, 3]) / (dirs[..., 2] - 0.2 * dirs[..., 0])
+    ok2 = mask2 > 0
+    assert ok2.mean() > 0.6 and np.abs(hint2[ok2] - t[ok2]).max() < 0.25 * 0.04
+    _, mask3, _ = ot.raycast_hint(vol, np.linalg.inv(K), T, ih, iw)   # default threshold 0.025: 4 far observations are not enough
+    assert mask3.sum() == 0
