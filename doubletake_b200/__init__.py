@@ -8,10 +8,13 @@ from .cost_volume import (CostVolumeManager, FastFeatureMeshHintVolumeManager, F
                           FeatureVolumeManager, MLP, to_b200)
 from .depth_model import DepthModel, DepthModelCVHint, HotPathOptions, install  # noqa: F401
 from .networks import BasicBlock, ConvPlan, CVEncoder, DepthDecoderPP, SkipDecoderRegression  # noqa: F401
+from .encoders import ResnetMatchingEncoder  # noqa: F401
+from . import formats  # noqa: F401
 from .tsdf import TSDF, TSDFFuser, get_frustum_bounds  # noqa: F401
 
 __all__ = [
     "CostVolumeManager", "FeatureVolumeManager", "FeatureMeshHintVolumeManager", "FastFeatureMeshHintVolumeManager",
     "MLP", "to_b200", "DepthModel", "DepthModelCVHint", "HotPathOptions", "install", "BasicBlock", "ConvPlan",
-    "CVEncoder", "DepthDecoderPP", "SkipDecoderRegression", "TSDF", "TSDFFuser", "get_frustum_bounds",
+    "CVEncoder", "DepthDecoderPP", "SkipDecoderRegression", "TSDF", "TSDFFuser", "get_frustum_bounds", "ResnetMatchingEncoder",
+    "formats",
 ]

@@ -72,6 +72,18 @@ class TsdfIntegrateParams(C.Structure):
     ]
 
 
+LAYOUT_F32, LAYOUT_SPLIT16 = 0, 1
+
+
+class InstanceNormParams(C.Structure):
+    _fields_ = [
+        ("src", fp), ("src_layout", C.c_int32), ("src_channels", C.c_int32), ("src_border", C.c_int32),
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("channels", C.c_int32),
+        ("eps", C.c_float), ("act", C.c_int32), ("act_slope", C.c_float),
+        ("dst", fp), ("dst_layout", C.c_int32), ("dst_border", C.c_int32), ("dst_nchw", fp), ("stats", fp),
+    ]
+
+
 class TsdfRaycastParams(C.Structure):
     _fields_ = [
         ("values", fp), ("weights", fp), ("dims", C.c_int32 * 3), ("origin_h", C.c_float * 3), ("voxel_size", C.c_float),
@@ -110,6 +122,9 @@ SYMBOLS = {
     "dtb200_relative_poses": (C.c_int, [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, fp]),
     "dtb200_exp": (C.c_int, [fp, fp, C.c_uint64, fp]),
     "dtb200_tsdf_integrate": (C.c_int, [C.POINTER(TsdfIntegrateParams), fp]),
+    "dtb200_encoder_stem": (C.c_int, [fp, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, fp]),
+    "dtb200_encoder_pool": (C.c_int, [fp, fp, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int32, fp]),
+    "dtb200_instance_norm": (C.c_int, [C.POINTER(InstanceNormParams), fp]),
     "dtb200_tsdf_raycast": (C.c_int, [C.POINTER(TsdfRaycastParams), fp]),
     "dtb200_tsdf_sample": (C.c_int, [fp, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_float, fp, fp, C.c_int64, C.c_int32, fp]),
 }

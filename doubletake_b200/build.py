@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdoubletake_b200.so")
-SOURCES = ["capi.cu", "cost_volume.cu", "cost_volume_tc.cu", "cost_volume_tch.cu", "conv_simt.cu", "conv_tc.cu", "conv_tch.cu", "conv_graph.cu", "tsdf.cu"]
+SOURCES = ["capi.cu", "cost_volume.cu", "cost_volume_tc.cu", "cost_volume_tch.cu", "conv_simt.cu", "conv_tc.cu", "conv_tch.cu", "conv_graph.cu", "tsdf.cu", "encoder.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

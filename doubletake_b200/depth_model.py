@@ -97,6 +97,10 @@ class DepthModelCVHint(nn.Module):
         if self.matching_model is None:
             raise RuntimeError("no matching encoder injected and no precomputed matching features in the data dicts")
         B, K = src_image.shape[:2]
+        if hasattr(self.matching_model, "forward_views"):
+            # the B200 encoder: every view in one pass, features already in the cost-volume kernels' layouts (its per-image
+            # InstanceNorm statistics make batching exact, so the reference's unbatched workaround is moot)
+            return self.matching_model.forward_views(cur_image, src_image)
         if unbatched_matching_encoder_forward:
             cur = self.matching_model(cur_image)
             src = torch.stack([self.matching_model(src_image[:, k]) for k in range(K)], 1)

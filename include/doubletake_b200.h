@@ -275,6 +275,43 @@ int dtb200_tsdf_integrate(const dtb200_tsdf_integrate_params* p, dtb200_stream_t
 int dtb200_tsdf_sample(const void* volume, const int32_t* dims, const float* origin_h, float voxel_size,
                        const float* world_points, float* out, int64_t num_points, int32_t mode, dtb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Matching-feature encoder: reference modules/networks.py:138-189 ResnetMatchingEncoder --
+ *   conv 7x7/2 + BN + ReLU (net.0-2)            -> dtb200_encoder_stem (BatchNorm folded into weight / bias by the caller)
+ *   MaxPool2d(2,1) + BlurPool(4,2) | MaxPool2d(3,2,1) (net.3) -> dtb200_encoder_pool
+ *   ResNet layer1, 1x1 conv, 3x3 conv           -> ordinary dtb200_conv2d descriptors (BatchNorm folded)
+ *   InstanceNorm2d [+ LeakyReLU] (net.6-7, net.9) -> dtb200_instance_norm, which can also write a replicate-padded map (so
+ *       that the padding_mode="replicate" 3x3 conv runs as a zero-padded conv on the enlarged map and is cropped again by
+ *       the next call's src_border) and the final features in the cost-volume kernels' layouts.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define DTB200_LAYOUT_F32 0      /* (N, H, W, C) fp32 */
+#define DTB200_LAYOUT_SPLIT16 1  /* (N, H, W, 2, C) fp16 big | small, see dtb200_nchw_to_split16 */
+
+/* dst (N, H/2, W/2, 64) fp32 NHWC = relu(conv7x7/2(image) + bias); weight_oihw (64,3,7,7) and bias (64) with the BatchNorm
+ * folded in; packed_weight: scratch of 147*64 floats (re-packed on every call, 9408 floats) */
+int dtb200_encoder_stem(const float* image_nchw, const float* weight_oihw, const float* bias, float* packed_weight,
+                        float* dst_nhwc, int n, int h, int w, dtb200_stream_t stream);
+/* src (N, h, w, c) fp32 NHWC -> dst in `dst_layout`; variant 0: MaxPool2d(2, stride 1) + BlurPool(filt 4, stride 2, reflect),
+ * output ((h-1+3-4)/2+1, ...) = (h/2, w/2) for even sizes; variant 1: MaxPool2d(3, stride 2, padding 1) */
+int dtb200_encoder_pool(const float* src_nhwc, void* dst, int32_t dst_layout, int n, int h, int w, int c, int32_t variant,
+                        dtb200_stream_t stream);
+
+typedef struct dtb200_instance_norm_params {
+  const void* src;        /* (N, H + 2*src_border, W + 2*src_border, src_channels) in src_layout; the border is skipped */
+  int32_t src_layout, src_channels, src_border;
+  int32_t batch, height, width;
+  int32_t channels;       /* the first `channels` (multiple of 4) channels of src are normalised and written */
+  float eps;              /* 1e-5 */
+  int32_t act;            /* DTB200_ACT_NONE or DTB200_ACT_LEAKY */
+  float act_slope;
+  void* dst;              /* (N, H + 2*dst_border, W + 2*dst_border, channels) in dst_layout, border = replicate padding; or NULL */
+  int32_t dst_layout, dst_border;
+  float* dst_nchw;        /* optional (N, channels, H, W) fp32 copy (needs dst_border == 0); or NULL */
+  float* stats;           /* scratch, N * channels * 2 floats (mean, 1/sqrt(var + eps)) */
+} dtb200_instance_norm_params;
+
+int dtb200_instance_norm(const dtb200_instance_norm_params* p, dtb200_stream_t stream);
+
 /* Rendered-depth hint of the incremental loop by ray casting the fused TSDF (mesh-free): one kernel
  * replaces reference marching cubes (tools/marching_cubes/marching_cubes.cu:164-424) + the mesh depth rasteriser
  * (utils/rendering_utils.py:25-53) + BackprojectDepth + TSDF.sample_tsdf + the threshold / NaN / mask rules of

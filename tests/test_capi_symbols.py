@@ -51,6 +51,7 @@ def test_struct_layout_matches_header_field_order():
     assert _struct_fields("dtb200_tsdf_frame") == [f[0] for f in _lib.TsdfFrame._fields_]
     assert _struct_fields("dtb200_tsdf_integrate_params") == [f[0] for f in _lib.TsdfIntegrateParams._fields_]
     assert _struct_fields("dtb200_tsdf_raycast_params") == [f[0] for f in _lib.TsdfRaycastParams._fields_]
+    assert _struct_fields("dtb200_instance_norm_params") == [f[0] for f in _lib.InstanceNormParams._fields_]
 
 
 def test_struct_sizes_and_offsets_match_the_c_compiler(tmp_path):
@@ -60,7 +61,7 @@ def test_struct_sizes_and_offsets_match_the_c_compiler(tmp_path):
 
     pairs = [("dtb200_conv_params", _lib.ConvParams), ("dtb200_cost_volume_params", _lib.CostVolumeParams),
              ("dtb200_tsdf_frame", _lib.TsdfFrame), ("dtb200_tsdf_integrate_params", _lib.TsdfIntegrateParams),
-             ("dtb200_tsdf_raycast_params", _lib.TsdfRaycastParams)]
+             ("dtb200_tsdf_raycast_params", _lib.TsdfRaycastParams), ("dtb200_instance_norm_params", _lib.InstanceNormParams)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "doubletake_b200.h")}"',
              "int main(void) {"]
     for cname, cls in pairs:

@@ -91,3 +91,21 @@ def test_tsdf_mirror_has_the_reference_signatures():
     rf = ref.TSDFFuser(ref.TSDF.from_bounds(dict(xmin=0, xmax=0.4, ymin=0, ymax=0.4, zmin=0, zmax=0.4), 0.05), use_gpu=False)
     assert (f.truncation, f.maxW, f.min_depth, f.max_depth, tuple(f.shape)) == \
            (rf.truncation, rf.maxW, rf.min_depth, rf.max_depth, tuple(rf.shape))
+
+
+@pytest.mark.parametrize("antialiased", [True, False])
+def test_matching_encoder_mirror_has_the_reference_state_dict(antialiased):
+    """doubletake_b200.ResnetMatchingEncoder vs the reference class (modules/networks.py:138-189; antialiased_cnns is the
+    restated stub): identical state_dict keys and shapes, strict round trip of the weights."""
+    import doubletake_b200 as dt
+    _ref_modules()
+    from doubletake.modules.networks import ResnetMatchingEncoder as Ref
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = Ref(18, 16, pretrained=False, antialiased=antialiased)
+    ours = dt.ResnetMatchingEncoder(18, 16, antialiased=antialiased)
+    rs, os_ = ref.state_dict(), ours.state_dict()
+    assert {k: tuple(v.shape) for k, v in rs.items()} == {k: tuple(v.shape) for k, v in os_.items()}
+    ours.load_state_dict(rs, strict=True)
+    assert all(torch.equal(rs[k], ours.state_dict()[k]) for k in rs)
+    assert list(ours.num_ch_enc) == list(ref.num_ch_enc) and ours.num_ch_out == ref.num_ch_out
