@@ -37,7 +37,49 @@ class MLP(nn.Module):
         self.net = nn.Sequential(*layers)
 
     def forward(self, x):
-        raise RuntimeError("doubletake_b200.MLP is evaluated inside the fused CUDA cost-volume kernel")
+        """Standalone evaluation (reference modules/networks.py:133-135): ``x`` of shape (..., F) -> (..., out).  On the hot
+        path these layers live inside the fused cost-volume kernel; called directly, the module runs them as 1x1 fused-conv
+        descriptors (exact fp32 math) over the flattened rows -- CUDA only, like everything here."""
+        from .networks import ConvPlan
+
+        if not x.is_cuda:
+            raise RuntimeError("doubletake_b200.MLP runs on CUDA only (no CPU fallback)")
+        linears = [m for m in self.net if isinstance(m, nn.Linear)]
+        acts = [isinstance(self.net[i + 1], nn.LeakyReLU) if i + 1 < len(self.net) else False
+                for i, m in enumerate(self.net) if isinstance(m, nn.Linear)]
+        lead, F = x.shape[:-1], x.shape[-1]
+        rows = x.reshape(-1, F).float()
+        n = rows.shape[0]
+        key = (n, str(x.device), tuple((l.weight._version, l.bias._version) for l in linears))
+        cache = self.__dict__.setdefault("_plan", {})
+        if key not in cache:
+            cache.clear()
+            plan = ConvPlan(x.device, "exact")
+            fpad = (F + 7) // 8 * 8                      # the SIMT conv reads input channels in groups of 8
+            f = plan.input("x", 1, fpad, 1, n)
+            holders = []
+            cin = fpad
+            for lin, act in zip(linears, acts):
+                out_c = lin.out_features
+                oc = out_c if (out_c % 64 == 0 or out_c < 64) else (out_c + 63) // 64 * 64
+                conv = nn.Conv2d(cin, oc, 1).to(x.device)
+                w = torch.zeros((oc, cin), device=x.device)
+                w[:out_c, : lin.in_features] = lin.weight.detach()
+                b = torch.zeros(oc, device=x.device)
+                b[:out_c] = lin.bias.detach()
+                conv.weight = nn.Parameter(w.view(oc, cin, 1, 1), requires_grad=False)
+                conv.bias = nn.Parameter(b, requires_grad=False)
+                holders.append(conv)
+                f = plan.conv([(f, L.RESAMPLE_NONE)], conv, L.ACT_LEAKY if act else L.ACT_NONE, 0.01)
+                cin = oc
+            plan.finalize()
+            cache[key] = (plan, f, holders, fpad, linears[-1].out_features)
+        plan, out, _, fpad, out_features = cache[key]
+        xin = torch.zeros((1, fpad, 1, n), device=x.device)
+        xin[0, :F, 0] = rows.t()
+        plan.load_inputs({"x": xin})
+        plan.run()
+        return plan.output_nchw(out)[0, :out_features, 0].t().reshape(*lead, out_features)
 
 
 class _PixelGrid(nn.Module):
@@ -305,8 +347,13 @@ def to_b200(manager, math="exact"):
     name = type(manager).__name__
     args = (manager.matching_height, manager.matching_width, manager.num_depth_bins)
     if hasattr(manager, "mlp"):
+        # F = (C + 10) K + C + 4 (feature_volume.py:48-70).  The reference managers do not store C or K; the fused kernels
+        # implement the reference's C = 16 (options.py matching_feature_dims), so K follows from F -- anything else is refused
         in_features = manager.mlp.net[0].weight.shape[1]
         K = (in_features - 20) // 26
+        if K < 1 or 26 * K + 20 != in_features:
+            raise ValueError(f"to_b200: an MLP input width of {in_features} is not (16 + 10) K + 20 for any K: the B200 kernels "
+                             "implement 16-channel matching features")
         cls = FeatureVolumeManager
         if hasattr(manager, "hint_mlp"):
             cls = FastFeatureMeshHintVolumeManager if name.startswith("Fast") else FeatureMeshHintVolumeManager

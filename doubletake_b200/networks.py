@@ -281,7 +281,21 @@ class BasicBlock(nn.Module):
         return plan.conv([(t, L.RESAMPLE_NONE)], self.conv2, L.ACT_LEAKY, 0.2, residual=skip)
 
     def forward(self, x):
-        raise RuntimeError("doubletake_b200.BasicBlock is executed through its parent's ConvPlan")
+        """Standalone evaluation (reference modules/layers.py:77-94): NCHW in, NCHW out, through a plan of this block's 2-3
+        descriptors.  Inside CVEncoder / DepthDecoderPP the block is emitted into the parent's plan instead."""
+        math = getattr(self, "math", "exact")
+        key = (tuple(x.shape), str(x.device), math, tuple(p._version for p in self.parameters()))
+        cache = self.__dict__.setdefault("_plan", {})
+        if key not in cache:
+            cache.clear()
+            plan = ConvPlan(x.device, math)
+            fx = plan.input("x", *x.shape)
+            out = self.emit(plan, [(fx, L.RESAMPLE_NONE)])
+            cache[key] = (plan.finalize(), out)
+        plan, out = cache[key]
+        plan.load_inputs({"x": x})
+        plan.run()
+        return plan.output_nchw(out)
 
 
 class _PlannedModule(nn.Module):

@@ -162,3 +162,22 @@ def test_large_map_3x3_conv_against_torch(B, H, W, chans, oc, math):
     assert hp.rel_err(got, want) < FEAT_TOL[math]
     # per-pixel check too: a wrong tap or a shifted row shows up as a large error on few pixels, not in the max norm only
     assert float((got - want).abs().max()) < 5e-5 * float(want.abs().max())
+
+
+def test_standalone_mlp_and_basic_block_forward():
+    """the reference's MLP and BasicBlock are callable modules; so are the mirrors (one-plan evaluation)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    mlp = dt.MLP([202, 128, 128, 1], disable_final_activation=True)
+    x = torch.randn(5, 7, 202, generator=g)
+    want = mlp.net[4](F.leaky_relu(mlp.net[2](F.leaky_relu(mlp.net[0](x), 0.01)), 0.01))
+    got = mlp.to(DEV)(x.to(DEV))
+    assert got.shape == (5, 7, 1) and hp.rel_err(got.cpu(), want) < 1e-5
+    for cin, cout, stride in ((64, 64, 1), (48, 64, 1), (64, 128, 2)):
+        blk = dt.BasicBlock(cin, cout, stride)
+        xb = torch.randn(2, cin, 20, 28, generator=g)
+        t = F.leaky_relu(blk.conv1(xb), 0.2)
+        skip = xb if blk.downsample is None else blk.downsample[0](xb)
+        want = F.leaky_relu(blk.conv2(t) + skip, 0.2)
+        got = blk.to(DEV)(xb.to(DEV))
+        assert got.shape == want.shape and hp.rel_err(got.cpu(), want) < 1e-5
