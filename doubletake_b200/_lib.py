@@ -97,6 +97,7 @@ class TsdfRaycastParams(C.Structure):
 SYMBOLS = {
     "dtb200_abi_version": (C.c_int, []),
     "dtb200_debug_set": (C.c_int, [C.c_int]),
+    "dtb200_debug_trace": (C.c_int, [C.c_void_p, C.c_int32]),
     "dtb200_last_error": (C.c_char_p, []),
     "dtb200_launch_count": (C.c_uint64, []),
     "dtb200_nchw_to_nhwc": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),

@@ -20,6 +20,7 @@ int launch_pack_tch(const float* oihw, float* packed, int out_c, int num_src, co
                     cudaStream_t s);                                                                     // conv_tch.cu
 uint64_t packed_floats_tch(int out_c, int num_src, const int32_t* src_c, int ksize);                     // conv_tch.cu
 uint64_t conv_tch_workspace_bytes(const dtb200_conv_params& p);                                          // conv_tch.cu
+int conv_tch_trace_set(unsigned long long* buf, int capacity);                                            // conv_tch.cu
 int launch_resample_copy_h(const dtb200_conv_params& p, cudaStream_t stream);                            // conv_tch.cu
 int launch_split16_transpose(const void* src, void* dst, int n, int c, int hw, bool to_split, cudaStream_t stream);  // conv_tch.cu
 
@@ -102,6 +103,9 @@ static int conv_total_in_c(const dtb200_conv_params& p, int& total) {
 using namespace dtb200;
 
 extern "C" int dtb200_debug_set(int flags) { return conv_tc_debug_set(flags); }
+extern "C" int dtb200_debug_trace(uint64_t* device_pairs, int32_t capacity) {
+  return conv_tch_trace_set(reinterpret_cast<unsigned long long*>(device_pairs), capacity);
+}
 extern "C" int dtb200_abi_version(void) { return DTB200_ABI_VERSION; }
 extern "C" const char* dtb200_last_error(void) { return g_error; }
 extern "C" uint64_t dtb200_launch_count(void) { return g_launches.load(); }

@@ -53,7 +53,8 @@ struct TcCfg {
 //   bit 2: previous split-K rule (many short items) instead of the round-count cost model
 //   bit 7: no halo-tile kernel (3x3 / stride-1 layers use the tap-major kernel too); bit 3: halo kernel with 1 tap per
 //          weight-ring stage instead of 3
-//   bits 8..12: timing knock-outs of the tensor-core conv pipeline (results are WRONG; tools/conv_bench.py --debug)
+//   bit 4: (tch) resident-weights halo kernel for 3x3 / stride-1 layers with <= 64 input and 64 output channels (conv_tch.cu)
+//   bits 8..13: timing knock-outs of the tensor-core conv pipeline (results are WRONG; tools/conv_bench.py --debug)
 static int g_flags = -1;
 // the timing knock-outs (bits 8 and up) make the kernels skip work, i.e. produce WRONG results: they are honoured only
 // when DTB200_DEVELOPMENT=1 is set in the environment (tools/conv_bench.py sets it), never by a stray debug_set call
@@ -73,6 +74,7 @@ static int conv_flags() {
   }
   return g_flags;
 }
+int conv_debug_flags() { return conv_flags(); }   // read by the tch kernels' knock-outs too
 int conv_tc_debug_set(int flags) {
   g_flags = sanitize_flags(flags);
   return DTB200_OK;

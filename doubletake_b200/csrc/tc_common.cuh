@@ -116,6 +116,64 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------- clusters / DSMEM / PDL
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster (prologue: makes every CTA's mbarrier init visible before a peer arrives on it)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of THIS CTA -> shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // release at cluster scope
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_acq_cluster(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return done != 0;
+}
+// bounded like mbar_wait; acquire at cluster scope (pairs with mbar_arrive_cluster of peer CTAs)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag) {
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_acq_cluster(addr, parity)) return;
+  const long long t0 = clock64();
+  for (;;) {
+    if (mbar_try_acq_cluster(addr, parity)) return;
+    const long long waited = clock64() - t0;
+    if (waited > 2000000000LL) {
+      if ((threadIdx.x & 31) == 0) printf("cluster mbar timeout: block %d warp %d tag %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), tag, parity);
+      if (waited > 2400000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ float4 ld_dsmem128(uint32_t cluster_addr) {
+  float4 v;
+  // volatile keeps the loads behind the cluster-scope acquire that precedes them; no "memory" clobber, so independent global
+  // loads of the epilogue (bias, residual) may be scheduled around them
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr));
+  return v;
+}
+__device__ __forceinline__ void prefetch_tensormap(const void* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
+// Programmatic dependent launch.  wait: returns once every prerequisite grid has completed and its writes are visible (at
+// once when the launch carries no programmatic edge).  launch_dependents: lets the runtime schedule the dependent grid as
+// soon as every CTA of this grid has issued it or exited -- the dependent's prologue then overlaps this grid's tail.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------- TMEM
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // one full warp
@@ -213,6 +271,14 @@ __device__ __forceinline__ void split_half2(float x0, float x1, uint32_t& big, u
   const __half2 s = __floats2half2_rn((x0 - bf.x) * kHalfSplitScale, (x1 - bf.y) * kHalfSplitScale);
   big = *reinterpret_cast<const uint32_t*>(&b);
   small = *reinterpret_cast<const uint32_t*>(&s);
+}
+// The same split with one saturating pack instead of four clamps (F2FP.SATFINITE): finite values beyond +-65504 saturate, NaN
+// stays NaN in both terms (the reference's convolutions propagate NaN too; an MMA row that holds a NaN is exactly the set of
+// outputs whose window contains it).  Used by the conv epilogues, where the split is the bulk of the per-element work.
+__device__ __forceinline__ void split_half2_sat(float x0, float x1, uint32_t& big, uint32_t& small) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(big) : "f"(x1), "f"(x0));
+  const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(&big));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(small) : "f"((x1 - bf.y) * kHalfSplitScale), "f"((x0 - bf.x) * kHalfSplitScale));
 }
 __device__ __forceinline__ float join_half(__half b, __half s) { return fmaf(__half2float(s), kHalfSplitInv, __half2float(b)); }
 

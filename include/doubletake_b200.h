@@ -37,6 +37,10 @@ int dtb200_abi_version(void);
 /* development only: kernel-variant switches of the tensor-core conv pipeline (0 = normal operation); the timing
  * knock-outs (bits 8 and up, wrong results by design) are ignored unless DTB200_DEVELOPMENT=1 is in the environment */
 int dtb200_debug_set(int flags);
+/* development only: timeline of the split16 ("tch") conv kernels.  `device_pairs` = capacity x 2 uint64 in device memory, caller
+ * initialises every pair to (UINT64_MAX, 0); each later tch conv launch takes the next pair (launch order, fixed at graph
+ * capture) and stamps %globaltimer: earliest CTA start, latest CTA end.  NULL turns it off.  tools/graph_trace.py */
+int dtb200_debug_trace(uint64_t* device_pairs, int32_t capacity);
 const char* dtb200_last_error(void);
 /* number of kernels this library has launched from the calling process (bench.py's gpu_launches claim) */
 uint64_t dtb200_launch_count(void);

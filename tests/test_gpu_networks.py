@@ -164,6 +164,43 @@ def test_large_map_3x3_conv_against_torch(B, H, W, chans, oc, math):
     assert float((got - want).abs().max()) < 5e-5 * float(want.abs().max())
 
 
+@pytest.mark.parametrize("chans,with_res", [((64,), True), ((24,), False), ((64,), False)])
+def test_resident_weights_halo_variant_against_torch(chans, with_res):
+    """The resident-weights halo kernel (development switch bit 4: weights of a <= 64-channel 3x3 layer stay in shared memory,
+    two MMA-issuing warps) on a map with >= 3 tiles per SM and ragged right / bottom tiles; the default (streaming) kernel on
+    the same inputs must agree with it to fp32 round-off."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(11)
+    H, W, oc = 200, 330, 64
+    x = torch.randn(1, chans[0], H, W, generator=g)
+    res = torch.randn(1, oc, H, W, generator=g)
+    conv = nn.Conv2d(chans[0], oc, 3, padding=1)
+    want = conv(x) + res if with_res else conv(x)
+    want = F.leaky_relu(want, 0.2)
+    outs = {}
+    try:
+        for flags in (16, 0):
+            L.check(L.lib().dtb200_debug_set(flags))
+            plan = dt.ConvPlan(torch.device(DEV), "tch")
+            fx = plan.input("x", *x.shape)
+            fr = plan.input("r", *res.shape) if with_res else None
+            o = plan.conv([(fx, L.RESAMPLE_NONE)], conv, L.ACT_LEAKY, 0.2, residual=fr)
+            plan.finalize()
+            plan.load_inputs({"x": x.to(DEV), **({"r": res.to(DEV)} if with_res else {})})
+            before = L.launch_count()
+            plan.run()
+            torch.cuda.synchronize()
+            assert L.launch_count() > before
+            outs[flags] = plan.output_nchw(o).cpu()
+    finally:
+        L.check(L.lib().dtb200_debug_set(0))
+    for got in outs.values():
+        assert hp.rel_err(got, want) < FEAT_TOL["tch"]
+        assert float((got - want).abs().max()) < 5e-5 * float(want.abs().max())
+    assert hp.rel_err(outs[16], outs[0]) < 2e-6
+
+
 def test_standalone_mlp_and_basic_block_forward():
     """the reference's MLP and BasicBlock are callable modules; so are the mirrors (one-plan evaluation)."""
     import torch.nn.functional as F

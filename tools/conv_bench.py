@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--math", default="tc3x")
     ap.add_argument("--only", default=None)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--burst", type=int, default=1, help="plan replays per event pair (CUDA events tick in ~2 us steps on this driver)")
+    ap.add_argument("--no-flush", action="store_true", help="L2-warm timing (inside a plan the producer's output is still in L2)")
     ap.add_argument("--debug", default="0", help="comma-separated dtb200_debug_set values, one pass per value")
     args = ap.parse_args()
     dev = torch.device("cuda")
@@ -71,13 +73,15 @@ def run(args, dev):
         torch.cuda.synchronize()
         ts = []
         for _ in range(args.reps):
-            flush.zero_()
+            if not args.no_flush:
+                flush.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            plan.run()
+            for _ in range(args.burst):
+                plan.run()
             e.record()
             torch.cuda.synchronize()
-            ts.append(s.elapsed_time(e))
+            ts.append(s.elapsed_time(e) / args.burst)
         ts.sort()
         ms = ts[len(ts) // 2]
         fl = plan.flops()
