@@ -58,8 +58,9 @@ __host__ __device__ inline int cvh_nkb1(int K) { return (K + 2) / 2; }   // ceil
 struct CvhSmall {
   ViewConst vc[DTB200_MAX_VIEWS];
   float b2[kHHidden], w3[kHHidden];
-  float hw[224];                 // hint MLP: hw1 (36) hb1 (12) hw2 (144) hb2 (12) hw3 (12) hb3 (1)
+  alignas(16) float hw[224];     // hint MLP: hw1 (36) hb1 (12) hw2 (144) hb2 (12) hw3 (12) hb3 (1); every part 16-byte aligned
   float partial[2][kHRows];
+  float h2x[6][kHRows];          // hint MLP hidden units 6..11 of every row, computed by the second epilogue half
   float score[kHRows];
   // a_empty is kept PER WRITER GROUP (0 = producers, 1 / 2 = epilogue column halves): the A ring is shared by three writer
   // groups and a parity wait is only sound if the waiter has observed every earlier phase of the barrier it waits on, so
@@ -103,9 +104,24 @@ __device__ __forceinline__ unsigned long long argmax_key(float v, int plane) {
   return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)plane);
 }
 
+// one K block of GEMM1 / GEMM2: KS x { D += A_small x W_big^T ; D += A_big x W_small^T ; D += A_big x W_big^T }
+template <int KS>
+__device__ __forceinline__ void cvh_issue_block(uint32_t tmem_d, uint32_t la_b, uint32_t la_s, uint32_t lb_b, uint32_t lb_s, bool acc0) {
+  constexpr uint32_t idesc = umma_idesc_f16(kHRows, kHHidden);
+  constexpr uint64_t hi = (uint64_t)(64u | (1u << 14) | (2u << 29)) << 32;   // SBO = 1024 B, version 1, SWIZZLE_128B
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const uint32_t ko = ks * 2;   // 16 fp16 = 32 bytes along K inside the swizzled row, in 16-byte units
+    umma_f16(tmem_d, hi | (la_s + ko), hi | (lb_b + ko), idesc, ks != 0 || acc0);
+    umma_f16(tmem_d, hi | (la_b + ko), hi | (lb_s + ko), idesc, true);
+    umma_f16(tmem_d, hi | (la_b + ko), hi | (lb_b + ko), idesc, true);
+  }
+}
+
 struct CvhWork {
   int pix_groups, plane_chunks;   // per batch element
   int total;                      // batch * pix_groups * plane_chunks (checked to fit 31 bits by the launcher)
+  int debug;                      // development: 0x1000 = CTA 0 prints a per-role timeline of its items 2..5
 };
 
 template <bool kHint, int kProdWarps>
@@ -124,6 +140,12 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
   CvhSmall& sm = *reinterpret_cast<CvhSmall*>(ring_b + SB * kHBStage);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // development timeline (debug bit 0x1000): clock64 at the hand-over points of items 2..5 of CTA 0
+  __shared__ long long tr[4][16];
+  __shared__ long long tr_t0;
+  const bool tracing = (wk.debug & 0x1000) && blockIdx.x == 0;
+#define CV_TRACE(it, idx) do { if (tracing && lane == 0 && (it) >= 2 && (it) < 6) tr[(it) - 2][idx] = clock64() - tr_t0; } while (0)
+  if (tid == 0) tr_t0 = clock64();
   const int K = p.views;
   const int nkb1 = cvh_nkb1(K);
   const int HW = p.height * p.width;
@@ -214,8 +236,10 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
 
     auto epi1 = [&](int it) {
       const int buf = it & 1;
+      if (warp == 0) CV_TRACE(it, 8);
       mbar_wait(&sm.d1_full[buf], (it >> 1) & 1, 20, 64);
       tc_fence_after();
+      if (warp == 0) CV_TRACE(it, 9);
       const uint32_t g = g2(it, half);
       const int st = (int)(g % S);
       wait_stage_free(1 + half, g, ebits, 21, 32);
@@ -239,12 +263,34 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_n(&sm.a_full[st], kProdWarps / 4);  // 4 warps fill one h1 block
+      if (warp == 0) CV_TRACE(it, 10);
     };
 
+    // epilogue-2 of an item: D2 -> +b2, LeakyReLU, . w3 (each warp its 64 columns) -> the two column halves meet in shared memory
+    // -> hint MLP -> volume store -> packed-key arg-max.  The hint MLP (3-12-12-1 per row, fp32, the reference's summation
+    // order) used to run on ONE thread per row with scalar shared-memory weight loads: 10 000 clk per item, as long as the
+    // producers' gathers (timeline, profiles/r02e_*).  Now both threads of a row (epilogue halves) compute six hidden units
+    // each from 16-byte weight loads, and the row's hint inputs are fetched before the wait for D2.
     auto epi2 = [&](int it) {
       const int buf = it & 1;
+      int b, pix0, d0;
+      decode(it, b, pix0, d0);
+      const int d = d0 + rdp, opix = pix0 + rpi;
+      float hin1 = -1.f, hin2 = 0.f;
+      if (kHint) {   // nearest-resized hint, |hint - plane depth| or -1, confidence (mesh_hint_volume.py:186-214)
+        const int ppix = min(opix, HW - 1);
+        const int py = ppix / p.width, px = ppix - py * p.width;
+        const int sy = min((int)floorf((float)py * ((float)p.hint_height / (float)p.height)), p.hint_height - 1);
+        const int sx = min((int)floorf((float)px * ((float)p.hint_width / (float)p.width)), p.hint_width - 1);
+        const long long o = ((long long)b * p.hint_height + sy) * p.hint_width + sx;
+        const bool valid = __ldg(p.hint_mask + o) != 0.f;
+        const float dd = plane_depth(p, b, min(d, p.planes - 1), ppix);
+        hin1 = valid ? fabsf(DT_SUB(__ldg(p.depth_hint + o), dd)) : -1.f;
+        hin2 = valid ? __ldg(p.hint_weights + o) : 0.f;
+      }
       mbar_wait(&sm.d2_full[buf], (it >> 1) & 1, 22, 64);
       tc_fence_after();
+      if (warp == 0) CV_TRACE(it, 11);
       float s = 0.f;
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
@@ -266,58 +312,77 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
       if (lane == 0) mbar_arrive(&sm.d2_empty[buf]);  // D2[buf] drained
       sm.partial[half][row] = s;
       named_bar(2, kHEpiWarps * 32);
-      if (half == 0) {
-        int b, pix0, d0;
-        decode(it, b, pix0, d0);
-        const int d = d0 + rdp, opix = pix0 + rpi;
-        float score = sm.partial[0][row] + sm.partial[1][row] + b3;
-        if (kHint) {
-          const int ppix = min(opix, HW - 1);
-          const int py = ppix / p.width, px = ppix - py * p.width;
-          const int sy = min((int)floorf((float)py * ((float)p.hint_height / (float)p.height)), p.hint_height - 1);
-          const int sx = min((int)floorf((float)px * ((float)p.hint_width / (float)p.width)), p.hint_width - 1);
-          const long long o = ((long long)b * p.hint_height + sy) * p.hint_width + sx;
-          const bool valid = __ldg(p.hint_mask + o) != 0.f;
-          const float dd = plane_depth(p, b, min(d, p.planes - 1), ppix);
-          const float in[3] = {score, valid ? fabsf(DT_SUB(__ldg(p.depth_hint + o), dd)) : -1.f, valid ? __ldg(p.hint_weights + o) : 0.f};
-          const float* hw1 = sm.hw, *hb1 = sm.hw + 36, *hw2 = sm.hw + 48, *hb2 = sm.hw + 192, *hw3 = sm.hw + 204;
-          float h1[12], h2[12];
+      float score = sm.partial[0][row] + sm.partial[1][row] + b3;
+      if (kHint) {
+        const float4* hw1 = reinterpret_cast<const float4*>(sm.hw);          // [12][3]
+        const float4* hb1 = reinterpret_cast<const float4*>(sm.hw + 36);
+        const float4* hw2 = reinterpret_cast<const float4*>(sm.hw + 48);     // [12][12]
+        const float* hb2 = sm.hw + 192;
+        float w1r[36], h1[12], h2[6];
 #pragma unroll
-          for (int o2 = 0; o2 < 12; ++o2) {
-            float a = hb1[o2];
+        for (int i = 0; i < 9; ++i) {
+          const float4 t = hw1[i];
+          w1r[4 * i] = t.x, w1r[4 * i + 1] = t.y, w1r[4 * i + 2] = t.z, w1r[4 * i + 3] = t.w;
+        }
 #pragma unroll
-            for (int i = 0; i < 3; ++i) a = DT_FMA(in[i], hw1[o2 * 3 + i], a);
-            h1[o2] = leaky01_fast(a);
+        for (int i = 0; i < 3; ++i) {
+          const float4 t = hb1[i];
+          h1[4 * i] = t.x, h1[4 * i + 1] = t.y, h1[4 * i + 2] = t.z, h1[4 * i + 3] = t.w;
+        }
+#pragma unroll
+        for (int o2 = 0; o2 < 12; ++o2) {   // a = hb1; a = fma(in[i], hw1[o2][i], a), i = 0..2
+          float a = h1[o2];
+          a = DT_FMA(score, w1r[o2 * 3], a);
+          a = DT_FMA(hin1, w1r[o2 * 3 + 1], a);
+          a = DT_FMA(hin2, w1r[o2 * 3 + 2], a);
+          h1[o2] = leaky01_fast(a);
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {       // hidden units 6 half .. 6 half + 5 of the second layer
+          const int o2 = 6 * half + j;
+          float a = hb2[o2];
+#pragma unroll
+          for (int i4 = 0; i4 < 3; ++i4) {
+            const float4 t = hw2[o2 * 3 + i4];
+            a = DT_FMA(h1[4 * i4], t.x, a);
+            a = DT_FMA(h1[4 * i4 + 1], t.y, a);
+            a = DT_FMA(h1[4 * i4 + 2], t.z, a);
+            a = DT_FMA(h1[4 * i4 + 3], t.w, a);
           }
+          h2[j] = leaky01_fast(a);
+        }
+        if (half == 1) {
 #pragma unroll
-          for (int o2 = 0; o2 < 12; ++o2) {
-            float a = hb2[o2];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) a = DT_FMA(h1[i], hw2[o2 * 12 + i], a);
-            h2[o2] = leaky01_fast(a);
-          }
+          for (int j = 0; j < 6; ++j) sm.h2x[j][row] = h2[j];
+        }
+        named_bar(2, kHEpiWarps * 32);
+        if (half == 0) {
+          const float* hw3 = sm.hw + 204;
           float a = sm.hw[216];
 #pragma unroll
-          for (int i = 0; i < 12; ++i) a = DT_FMA(h2[i], hw3[i], a);
+          for (int i = 0; i < 6; ++i) a = DT_FMA(h2[i], hw3[i], a);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) a = DT_FMA(sm.h2x[i][row], hw3[6 + i], a);
           score = a;
         }
+      }
+      if (half == 0) {
         if (d < p.planes && opix < HW) p.volume[((long long)b * p.planes + d) * HW + opix] = score;
         sm.score[row] = score;
       }
       named_bar(2, kHEpiWarps * 32);
       if (warp == 0 && lane < kHPix) {
-        int b, pix0, d0;
-        decode(it, b, pix0, d0);
-        const int opix = pix0 + lane;
-        if (opix < HW) {
+        const int opx = pix0 + lane;
+        if (opx < HW) {
           unsigned long long best = 0ull;
           for (int w = 0; w < kHPlanes && d0 + w < p.planes; ++w) {
             const unsigned long long k = argmax_key(sm.score[w * kHPix + lane], d0 + w);
             best = k > best ? k : best;
           }
-          atomicMax(keys + (long long)b * HW + opix, best);
+          atomicMax(keys + (long long)b * HW + opx, best);
         }
       }
+      if (warp == 0) CV_TRACE(it, 12);
     };
 
     for (int it = 0; it < n; ++it) {
@@ -335,10 +400,16 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
     const uint32_t ring_u = smem_u32(ring_a);
     int cur_b = -1;
     uint32_t pbits = 0;   // per-stage wait parities of the producer group
+    int st_b = -1, st_pix0 = -1;   // pixel group whose per-pixel state the registers below hold
+    float ray[kRowsPerThread][3];
+    float4 cur[kRowsPerThread];
+    int pixs[kRowsPerThread];
+    bool live[kRowsPerThread];
 
     for (int it = 0; it < n; ++it) {
       int b, pix0, d0;
       decode(it, b, pix0, d0);
+      if (warp == kHEpiWarps) CV_TRACE(it, 0);
       if (b != cur_b) {  // (re)load the per-view constants of this batch element
         named_bar(1, kProdThreads);
         if (pt < K)
@@ -347,23 +418,31 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
         named_bar(1, kProdThreads);
         cur_b = b;
       }
-      // ---- per-row state
+      // ---- per-row state.  Consecutive items of a CTA are the same 16 pixels with the next 8 planes: the pixel's ray, its
+      // current-view features and indices are computed once per pixel group (their dependent global loads cost 2900 clk per
+      // item in the timeline), only the depth-dependent part per item
       float X[kRowsPerThread][3], an[kRowsPerThread][3], rc[kRowsPerThread][3], depth[kRowsPerThread];
-      float4 cur[kRowsPerThread];
-      int pixs[kRowsPerThread];
-      bool live[kRowsPerThread], lastp[kRowsPerThread], any_d[kRowsPerThread], any_b[kRowsPerThread];
+      bool lastp[kRowsPerThread], any_d[kRowsPerThread], any_b[kRowsPerThread];
+      if (b != st_b || pix0 != st_pix0) {
+        st_b = b, st_pix0 = pix0;
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerThread; ++rr) {
+          const int row = rbase + 64 * rr;
+          const int pix = pix0 + (row & 15);
+          live[rr] = pix < HW;
+          const int pixc = live[rr] ? pix : HW - 1;
+          pixs[rr] = pix;
+          const int y = pixc / p.width, x = pixc - y * p.width;
+          backproject_ray(p.cur_invK + b * 16, x, y, ray[rr]);
+          const float* c = p.cur_feats + ((long long)b * kC + q * 4) * HW + pixc;
+          cur[rr] = make_float4(__ldg(c), __ldg(c + HW), __ldg(c + 2 * HW), __ldg(c + 3 * HW));
+        }
+      }
 #pragma unroll
       for (int rr = 0; rr < kRowsPerThread; ++rr) {
         const int row = rbase + 64 * rr;
-        const int pix = pix0 + (row & 15);
-        live[rr] = pix < HW;
-        const int pixc = live[rr] ? pix : HW - 1;
-        pixs[rr] = pix;
-        const int y = pixc / p.width, x = pixc - y * p.width;
-        float r[3];
-        backproject_ray(p.cur_invK + b * 16, x, y, r);
-        const float* c = p.cur_feats + ((long long)b * kC + q * 4) * HW + pixc;
-        cur[rr] = make_float4(__ldg(c), __ldg(c + HW), __ldg(c + 2 * HW), __ldg(c + 3 * HW));
+        const int pixc = live[rr] ? pixs[rr] : HW - 1;
+        const float* r = ray[rr];
         const int dreal = d0 + (row >> 4);
         const int d = min(dreal, p.planes - 1);
         lastp[rr] = (dreal == p.planes - 1);
@@ -388,6 +467,7 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
         const int stA = (int)(gA % S), stB = (int)(gB % S);
         wait_stage_free(0, gA, pbits, 10, 64);
         if (has_b) wait_stage_free(0, gB, pbits, 11, 64);
+        if (warp == kHEpiWarps) CV_TRACE(it, 1 + 2 * pass);
         const uint32_t baseA = ring_u + (uint32_t)stA * kHAStage, baseB = ring_u + (uint32_t)stB * kHAStage;
         const int my_slot = 4 * pass + q;   // the slot whose per-(row, view) scalar work this lane does
 #pragma unroll
@@ -476,6 +556,7 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
           mbar_arrive(&sm.a_full[stA]);
           if (has_b) mbar_arrive(&sm.a_full[stB]);
         }
+        if (warp == kHEpiWarps) CV_TRACE(it, 2 + 2 * pass);
       }
       // ---- any-view mask of the last plane: the 4 lanes of a quad own different slots of every pass
 #pragma unroll
@@ -501,14 +582,13 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
       const uint32_t a_big = ring_a_u + (uint32_t)st * kHAStage, a_small = a_big + kHTile;
       const uint32_t b_big = ring_b_u + (uint32_t)sb * kHBStage, b_small = b_big + kHTile;
       if (elect_one()) {
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t ko = (uint32_t)ks * 32u;   // 16 fp16 = 32 bytes along K inside the swizzled row
-          const uint64_t da_b = umma_desc_k128(a_big + ko), da_s = umma_desc_k128(a_small + ko);
-          const uint64_t db_b = umma_desc_k128(b_big + ko), db_s = umma_desc_k128(b_small + ko);
-          umma_f16(tmem_d, da_s, db_b, idesc, !(first && ks == 0));
-          umma_f16(tmem_d, da_b, db_s, idesc, true);
-          umma_f16(tmem_d, da_b, db_b, idesc, true);
-        }
+        // compile-time K-step counts, fully unrolled: a run-time trip count costs two R2UR, a compare and two branches per MMA
+        // (~88 clk per issue where the pipe needs 64; conv_tch.cu has the measurement)
+        const bool acc0 = !first;
+        const uint32_t la_b = ((a_big & 0x3FFFFu) >> 4) | (1u << 16), la_s = ((a_small & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t lb_b = ((b_big & 0x3FFFFu) >> 4) | (1u << 16), lb_s = ((b_small & 0x3FFFFu) >> 4) | (1u << 16);
+        if (ksteps == 4) cvh_issue_block<4>(tmem_d, la_b, la_s, lb_b, lb_s, acc0);
+        else cvh_issue_block<2>(tmem_d, la_b, la_s, lb_b, lb_s, acc0);
         const int next_writer = writer_of(g + S);
         if (next_writer >= 0) umma_commit(&sm.a_empty[next_writer][st]);
         umma_commit(&sm.b_empty[sb]);
@@ -518,18 +598,22 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
     };
     auto gemm1 = [&](int it) {
       const uint32_t d1 = tmem_u + (uint32_t)((it & 1) * kHHidden);
+      CV_TRACE(it, 5);
       for (int kb = 0; kb < nkb1; ++kb) {
         const int slots = min(2, K + 1 - 2 * kb);
         block(g1(it, kb), 2 * slots, d1, kb == 0, kb == nkb1 - 1 ? &sm.d1_full[it & 1] : nullptr);
       }
+      CV_TRACE(it, 6);
     };
     auto gemm2 = [&](int it) {
       const int buf = it & 1;
       mbar_wait(&sm.d2_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 42, 20);  // epilogue-2 of item it-2 has drained D2[buf]
       tc_fence_after();
       const uint32_t d2 = tmem_u + (uint32_t)(2 * kHHidden + buf * kHHidden);
+      CV_TRACE(it, 13);
       block(g2(it, 0), 4, d2, true, nullptr);
       block(g2(it, 1), 4, d2, false, &sm.d2_full[buf]);
+      CV_TRACE(it, 7);
     };
     for (int it = 0; it < n; ++it) {
       gemm1(it);
@@ -560,6 +644,15 @@ __global__ void __launch_bounds__((kHEpiWarps + kProdWarps + 2) * 32, 1)
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
+  if (tracing && tid == 0) {
+    printf("cv_mlp_tch trace (clk since kernel start, CTA 0, %d items, K = %d): end %lld\n", n, K, clock64() - tr_t0);
+    for (int i = 0; i < 4 && i + 2 < n; ++i)
+      printf("  item %d: producer start %lld, pass0 [%lld %lld] pass1 [%lld %lld] | mma gemm1 [%lld %lld] gemm2 [%lld %lld] | epi1 [%lld wait-> %lld %lld] "
+             "epi2 [%lld %lld]\n",
+             i + 2, tr[i][0], tr[i][1], tr[i][2], tr[i][3], tr[i][4], tr[i][5], tr[i][6], tr[i][13], tr[i][7], tr[i][8], tr[i][9], tr[i][10], tr[i][11],
+             tr[i][12]);
+  }
+#undef CV_TRACE
 }
 
 // arg-max keys -> best_index / lowest_cost (the plane depth at the arg-max, cost_volume.py:356-361)
@@ -698,6 +791,8 @@ static int g_cvh_sms[64] = {0};
 static std::once_flag g_cvh_once[64];
 static int g_cvh_variant = -1;   // producer warps: 8 or 16 (DTB200_CV_PRODUCERS, development switch)
 
+int conv_debug_flags();   // conv_tc.cu (development switches)
+
 int launch_cost_volume_tch(const dtb200_cost_volume_params& p, cudaStream_t stream) {
   if (!p.workspace || p.workspace_bytes < cost_volume_tch_workspace_bytes(p))
     return fail(DTB200_ERR_INVALID, "cost volume (tch): workspace missing/too small (dtb200_cost_volume_workspace_bytes)%s");
@@ -729,6 +824,7 @@ int launch_cost_volume_tch(const dtb200_cost_volume_params& p, cudaStream_t stre
   const long long total_items = (long long)p.batch * wk.pix_groups * wk.plane_chunks;
   if (total_items > 0x3FFFFFFFLL) return fail(DTB200_ERR_UNSUPPORTED, "cost volume (tch): too many work items%s");
   wk.total = (int)total_items;
+  wk.debug = conv_debug_flags() & ~0xff;
   uint8_t* ws = reinterpret_cast<uint8_t*>(p.workspace);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + cvh_weight_bytes(p.views));
   cudaError_t e = cudaMemsetAsync(keys, 0, (size_t)p.batch * HW * 8, stream);
