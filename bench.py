@@ -41,6 +41,10 @@ WORKLOADS = {
     "cfg3": ("depth frames/sec at 512x384x48planes x5views, batch 8 (DoubleTake-small)",
              "cfg3: DoubleTake-small 512x384 image, 96x128x16 matching feats, 48 planes, 5 src views, hint on, batch 8 per GPU, "
              "CVEncoder+SkipDecoderRegression (resnet18d priors)"),
+    "cfg4": ("depth frames/sec over the ScanNetv2 test split shapes (512x384, 64 planes, 7 views), keyframes sharded round-robin",
+             "cfg4: DoubleTake 512x384 image, 96x128x16 matching feats, 64 planes, 7 src views, hint on, one keyframe per rank per step "
+             "taken from this rank's shard of the 25 590-tuple / 100-scan ScanNetv2 test split (synthetic tensors per tuple), NCCL "
+             "depth-map gather batched every --gather-every keyframes"),
     "cfg5": ("depth frames/sec at 1024x768x96planes x9views, batch 4 (stress)",
              "cfg5: synthetic stress 1024x768 image, 192x256x16 matching feats, 96 planes, 9 src views, hint on, batch 4 per GPU, "
              "CVEncoder+DepthDecoderPP (effnetv2-s priors)"),
@@ -241,7 +245,26 @@ def run_b200(args):
     depth_shape = (cfg.batch, 1, cfg.image_h // 2, cfg.image_w // 2)
     host_out = torch.empty(depth_shape, dtype=torch.float32).pin_memory()
 
+    # cfg 4: this rank's keyframes of the tuple list (round-robin, or whole scans for the incremental variant); a step is the
+    # next keyframe of the shard, its synthetic tensors picked by the tuple; depth maps are parked and gathered every G keyframes
+    shard = None
+    if args.workload == "cfg4":
+        tuples = sharding.synthetic_scannet_test_tuples()
+        shard = sharding.shard_tuples(tuples, rank, world, by=args.shard_by)
+        G = max(1, args.gather_every)
+        parked = torch.empty((G,) + depth_shape[1:], dtype=torch.float32, device=dev)
+
     def step_resident(i):
+        if shard is not None:
+            t = shard[i % len(shard)]
+            cur, src = dev_sets[(t * 2654435761 >> 7) % n_sets]
+            out = model("test", cur, src, return_mask=True)
+            depth = out["depth_pred_s0_b1hw"]
+            if world > 1:
+                parked[i % G].copy_(depth[0])
+                if (i + 1) % G == 0:
+                    depth = sharding.gather_depth_maps(parked, G * world)
+            return depth
         cur, src = dev_sets[i % n_sets]
         out = model("test", cur, src, return_mask=True)
         depth = out["depth_pred_s0_b1hw"]
@@ -252,11 +275,20 @@ def run_b200(args):
     def step_e2e(i):
         # pinned HOST dicts go straight into the public API: forward() stages them on its copy stream (matching features
         # and hint first, prior maps while the cost volume runs) -- every byte is copied inside the timed region
-        cur, src = host_sets[i % n_sets]
+        if shard is not None:
+            t = shard[i % len(shard)]
+            cur, src = host_sets[(t * 2654435761 >> 7) % n_sets]
+        else:
+            cur, src = host_sets[i % n_sets]
         out = model("test", cur, src, return_mask=True)
         depth = out["depth_pred_s0_b1hw"]
         if world > 1:
-            depth = sharding.gather_depth_maps(depth, frames_per_step)
+            if shard is not None:
+                parked[i % G].copy_(depth[0])
+                if (i + 1) % G == 0:
+                    sharding.gather_depth_maps(parked, G * world)
+            else:
+                depth = sharding.gather_depth_maps(depth, frames_per_step)
         host_out.copy_(depth[: cfg.batch], non_blocking=True)
         return depth
 
@@ -357,7 +389,10 @@ def run_b200(args):
             "config": {"workload": workload_desc, "math": args.math, "volume_math": volume_math, "frames_per_step": frames_per_step,
                        "l2": "256 MiB L2 flush between timed steps (outside the per-step event pairs); 4 rotating input sets",
                        "weights": "random-init (seeded), reference architecture",
-                       "wall_ms_per_step_incl_flush": round(1e3 * t_wall / args.steps, 4)},
+                       "wall_ms_per_step_incl_flush": round(1e3 * t_wall / args.steps, 4),
+                       **({"tuples": len(tuples), "shard_by": args.shard_by, "keyframes_this_rank": len(shard),
+                           "gather_every": G, "full_split_seconds_at_this_rate": round(len(tuples) / value, 1)}
+                          if shard is not None else {})},
             "e2e": {"value": round(frames_per_step * args.steps / e2e_s, 3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": host_out.numel() * 4},
             "gpu_launches": int(launches),
@@ -615,6 +650,9 @@ def main():
                     help="cost-volume MLP arithmetic; default: tch (kind::f16, 2-term fp16 split) unless --math exact")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
                     help="cfg2 = the headline metric's configuration (default); cfg3 / cfg5 = BASELINE.json configs[2] / [4]")
+    ap.add_argument("--gather-every", type=int, default=16, help="cfg4: keyframes per rank between two depth-map gathers")
+    ap.add_argument("--shard-by", default="frame", choices=["frame", "scan"],
+                    help="cfg4: round-robin keyframes, or whole scans per rank (the incremental mode's constraint)")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back steps for the `sustained` figure (0 = off)")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the eager-PyTorch-on-this-GPU reference timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")

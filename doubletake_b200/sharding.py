@@ -50,6 +50,22 @@ def read_frame_tuples(path, limit_to_scan_id=None, skip_to_frame=None, skip_fram
     return out
 
 
+def synthetic_scannet_test_tuples():
+    """A stand-in for the reference's ScanNetv2 test tuple file with the SAME scans and per-scan keyframe counts (25 590 tuples
+    over 100 scans, data/scannetv2_test_tuple_counts.json), for boxes where the reference tree does not exist: frame ids are
+    synthetic (keyframe j of a scan reads frames 10 j, 10 j - 10, ...), the sharding sees exactly the real structure."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "scannetv2_test_tuple_counts.json")) as f:
+        meta = json.load(f)
+    out = []
+    for scan_id, count in meta["scans"]:
+        for j in range(count):
+            out.append((scan_id, [f"{max(10 * (j + 1) - 10 * v, 0):06d}" for v in range(meta["views"])]))
+    return out
+
+
 def shard_tuples(tuples, rank: int, world_size: int, by: str = "frame"):
     """Indices (into ``tuples``) of the keyframes this rank processes, in processing order.
 

@@ -53,6 +53,8 @@ CONFIGS = {
     "cfg3": WorkloadConfig(
         "cfg3", 8, 5, 384, 512, 48, hint=True, prior_ch=(64, 64, 128, 256, 512), decoder="skip", seed=1003
     ),
+    # cfg 4: ScanNetv2 test-split shapes (the reference's default 512x384 input, options.py:69-70), DoubleTake, one keyframe per step
+    "cfg4": WorkloadConfig("cfg4", 1, 7, 384, 512, 64, hint=True, seed=1004),
     # cfg 5: synthetic stress
     "cfg5": WorkloadConfig("cfg5", 4, 9, 768, 1024, 96, hint=True, seed=1005),
     # small variants for tests / golden fixtures
