@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, call 40: cluster split-K exchanged through L2 scratch instead of distributed shared memory: parity, timeline, A/B bench
+# Round 2, call 41: cluster split-K through an L2 scratch, staged rows copied out coalesced, batched reduce loads: parity, timeline, A/B bench
 O=gpurun_out
 mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_networks.py tests/test_gpu_model.py tests/test_gpu_encoder.py tests/test_gpu_full_size.py -q -x > $O/u2_pytest.txt 2>&1; echo "pytest rc=$?"; tail -3 $O/u2_pytest.txt
