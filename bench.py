@@ -453,6 +453,17 @@ def kernel_rooflines(model, dev_sets, cfg, flush, L, reps=9):
                                            src["K_s1_b44"], cur["invK_s1_b44"], mn, mx, cur, None, True)
 
     cv_ms = time_fn(run_cv)
+    # the dot-product volume (CostVolumeManager, the SimpleRecon-style matcher) on the same features: the kernel the north star's
+    # HBM target names; not part of the DoubleTake step, timed for the record
+    import doubletake_b200 as dt
+
+    dot_mgr = dt.CostVolumeManager(cfg.match_h, cfg.match_w, cfg.planes).to(dev)
+
+    def run_dot():
+        dot_mgr._run(cur["matching_feats_bchw"], src["matching_feats_bkchw"], ext, pose, src["K_s1_b44"], cur["invK_s1_b44"], mn, mx,
+                     None, None, False)
+
+    dot_ms = time_fn(run_dot)
     plan = model._network_plan(cv["out"]["volume"].shape, cur["image_prior_feats"])
     conv_ms = time_fn(plan.run)
     n_conv = len(plan.ops)
@@ -481,16 +492,23 @@ def kernel_rooflines(model, dev_sets, cfg, flush, L, reps=9):
             "algorithmic_flops": conv_flops, "peak_source": peaks["src"] + " bf16 burst (graph replay timed alone)",
             "frac_of_sustained_peak": round(conv_flops / (conv_ms * 1e-3) / 1e12 / tens_sustained, 5)},
     }
+    dot_bytes = algorithmic_bytes_cost_volume(cfg, hint=False)
+    entries["cost_volume_dot"] = {
+        "bound": "hbm", "achieved": round(dot_bytes / (dot_ms * 1e-3) / 1e9, 2), "peak": peaks["hbm"], "unit": "GB/s",
+        "frac": round(dot_bytes / (dot_ms * 1e-3) / 1e9 / peaks["hbm"], 5), "traffic": None, "ms_per_launch": round(dot_ms, 4),
+        "launches_per_step": 0, "algorithmic_bytes": dot_bytes, "peak_source": peaks["src"] + " HBM copy",
+        "note": "CostVolumeManager (dot-product matcher) at this workload's shapes; instruction-issue bound, not HBM bound "
+                "(profiles/r02c_cv_sweep.txt); not part of the timed step"}
     # context for `frac`: an fp32-accurate tensor-core path issues 3 MMAs per product -- TF32 ones at half the bf16 rate
     # (ceiling = peak / 6) or, with the fp16 split, f16 ones at the full rate (ceiling = peak / 3); reported next to the
     # contract's frac-of-bf16-peak, never instead of it
     maths = {"conv_stack": model.math, "cost_volume_mlp_hint": model.volume_math}
     for name, e in entries.items():
-        div = {"tc3x": 6.0, "tch": 3.0}.get(maths[name])
+        div = {"tc3x": 6.0, "tch": 3.0}.get(maths.get(name))
         if div:
             e["split_ceiling"] = round(tens_peak / div, 1)
             e["frac_of_split_ceiling"] = round(e["achieved"] / (tens_peak / div), 4)
-            e["split"] = {"tc3x": "3xTF32", "tch": "2-term fp16, 3 MMAs"}[maths[name]]
+            e["split"] = {"tc3x": "3xTF32", "tch": "2-term fp16, 3 MMAs"}[maths.get(name)]
     dom = "conv_stack" if conv_ms >= cv_ms else "cost_volume_mlp_hint"
     d = dict(entries[dom])
     d["kernel"] = dom
