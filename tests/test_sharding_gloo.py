@@ -50,3 +50,41 @@ def test_gather_even_split():
 
 def test_gather_ragged_split():
     _run(5)
+
+
+def _worker_batched(rank, world, port, q):
+    """bench.py --workload cfg4: every rank parks G keyframes of its round-robin shard of the tuple list and gathers them in one
+    collective; gathered block g must hold global keyframes g*G*world .. (g+1)*G*world - 1 in tuple order."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tuples = sharding.synthetic_scannet_test_tuples()[:40]
+        shard = sharding.shard_tuples(tuples, rank, world, by="frame")
+        G = 4
+        ok = True
+        parked = torch.empty(G, 1, 3, 4)
+        for i, t in enumerate(shard[: 3 * G]):
+            parked[i % G] = float(t) + 0.25          # the "depth map" of keyframe t
+            if (i + 1) % G == 0:
+                full = sharding.gather_depth_maps(parked, G * world)
+                block = (i + 1) // G - 1
+                expect = torch.stack([torch.full((1, 3, 4), k + 0.25) for k in range(block * G * world, (block + 1) * G * world)])
+                ok = ok and bool(torch.equal(full, expect))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_batched_gather_of_sharded_keyframes_is_in_tuple_order():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_batched, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in results), results
